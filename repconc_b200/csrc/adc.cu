@@ -1,0 +1,710 @@
+// adc.cu -- PQ asymmetric-distance (inner-product) top-k search over the coded corpus.
+// Reference: src/repconc/models/repconc/evaluate_repconc.py:78-98,180-206 (Faiss IndexPQ,
+// METRIC_INNER_PRODUCT, nbits = 8) and src/repconc/models/jpq/finetune_jpq.py:176.
+//
+// Data layout in HBM
+//   codes   (N, M) uint8, row-major -- exactly the bytes of Faiss' IndexPQ.codes / the reference's
+//           `add_docs` input; a document is M consecutive bytes (48 B at M = 48)
+//   lut     (nq, M, 256) fp32, <x_q[m,:], c[m,k,:]>
+//   scores  never materialised for the full corpus: the scan keeps, per query, only documents whose
+//           score reaches a threshold estimated from a strided sample of the corpus
+//
+// Kernels
+//   adc_lut_kernel      inner-product tables
+//   adc_scan_kernel     the hot loop.  One CTA holds the LUTs of QT queries interleaved in shared
+//                       memory ([m][k][QT], one LDS.128 serves 4 queries), one thread owns one
+//                       document: its M code bytes are loaded once (vectorised, coalesced) into
+//                       registers and reused for the QT queries; accumulation is fp32, m ascending
+//                       (bit-identical to a sequential CPU scan).  Epilogue either stores dense
+//                       scores (sample / small corpora / exact fallback) or appends (score, id) to the
+//                       query's candidate list when score >= threshold.
+//   select/gather/sort  exact top-k: 4-pass radix select over fp32 keys, tie-exact ordered gather,
+//                       bitonic sort of <= 8192 composite keys (score desc, id asc).
+#include <float.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rc {
+
+constexpr int ADC_K = 256;
+constexpr int SCAN_THREADS = 512;
+constexpr int SEL_THREADS = 1024;
+constexpr int CAND_CAP = 8192;        // candidate list capacity per query == max sortable k
+constexpr int Q_CHUNK = 1024;         // queries processed per pass of the host loop
+constexpr int FB_ROWS = 4;            // exact-fallback queries per dense scan
+constexpr int64_t DENSE_N_MAX = 262144;  // corpora up to this size take the dense path
+constexpr int SAMPLE_BLK = 1024;      // sample = evenly spaced blocks of this many documents
+
+// ---------------------------------------------------------------------------------------------
+// LUT
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adc_lut_kernel(const float* __restrict__ queries, int64_t ldq, const float* __restrict__ c, int M, int ds,
+               float* __restrict__ lut) {
+    extern __shared__ float qs[];  // ds floats
+    const int64_t q = blockIdx.x;
+    const int m = blockIdx.y;
+    for (int j = threadIdx.x; j < ds; j += blockDim.x) qs[j] = queries[q * ldq + (int64_t)m * ds + j];
+    __syncthreads();
+    const int k = threadIdx.x;
+    const float* ck = c + ((int64_t)m * ADC_K + k) * ds;
+    float s = 0.0f;
+    for (int j = 0; j < ds; ++j) s = __fadd_rn(s, __fmul_rn(qs[j], __ldg(ck + j)));
+    lut[(q * M + m) * ADC_K + k] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan
+// ---------------------------------------------------------------------------------------------
+template <int QT> struct LutVec;
+template <> struct LutVec<1> { using type = float; };
+template <> struct LutVec<2> { using type = float2; };
+template <> struct LutVec<4> { using type = float4; };
+
+template <int QT>
+__device__ __forceinline__ void lut_add(float (&acc)[QT], const typename LutVec<QT>::type& v);
+template <> __device__ __forceinline__ void lut_add<1>(float (&acc)[1], const float& v) { acc[0] += v; }
+template <> __device__ __forceinline__ void lut_add<2>(float (&acc)[2], const float2& v) {
+    acc[0] += v.x; acc[1] += v.y;
+}
+template <> __device__ __forceinline__ void lut_add<4>(float (&acc)[4], const float4& v) {
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+}
+
+struct ScanArgs {
+    const float* lut;        // (nq, M, 256)
+    const uint8_t* codes;    // (N, M)
+    int64_t nq;
+    int64_t npos;            // positions to scan (documents, or sample positions)
+    int64_t pos_per_split;   // positions per blockIdx.y
+    int64_t blk, stride;     // blk == 0: doc = n0 + pos ; else doc = (pos / blk) * stride + pos % blk
+    int64_t n0;
+    int M;
+    // dense epilogue
+    float* out; int64_t ld_out;
+    // filter epilogue
+    const float* thr; unsigned int* cnt; unsigned long long* cand; int cap;
+};
+
+__device__ __forceinline__ unsigned long long pack_cand(float score, uint32_t doc) {
+    return ((unsigned long long)f32_to_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
+}
+
+template <int QT, int MT, bool FILTER>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+adc_scan_kernel(ScanArgs a) {
+    using V = typename LutVec<QT>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* lutS = reinterpret_cast<V*>(smem_raw);  // [M][256]
+    const int M = MT > 0 ? MT : a.M;
+    const int64_t q0 = (int64_t)blockIdx.x * QT;
+    const int nqt = (int)min((int64_t)QT, a.nq - q0);
+
+    // stage the QT look-up tables, interleaved per (m,k)
+    {
+        float* lf = reinterpret_cast<float*>(smem_raw);
+        const int n = M * ADC_K;
+        for (int qq = 0; qq < QT; ++qq) {
+            const float* src = a.lut + (q0 + qq) * (int64_t)n;
+            for (int i = threadIdx.x; i < n; i += SCAN_THREADS) lf[i * QT + qq] = qq < nqt ? __ldg(src + i) : 0.0f;
+        }
+    }
+    float thr[QT];
+#pragma unroll
+    for (int qq = 0; qq < QT; ++qq) thr[qq] = (FILTER && qq < nqt) ? a.thr[q0 + qq] : 0.0f;
+    __syncthreads();
+
+    const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
+    const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
+    for (int64_t p = p_lo + threadIdx.x; p < p_hi; p += SCAN_THREADS) {
+        const int64_t doc = a.blk == 0 ? a.n0 + p : (p / a.blk) * a.stride + (p % a.blk);
+        const uint8_t* cp = a.codes + doc * M;
+        float acc[QT];
+#pragma unroll
+        for (int qq = 0; qq < QT; ++qq) acc[qq] = 0.0f;
+        if constexpr (MT > 0 && MT % 16 == 0) {
+            uint4 w[MT / 16];
+#pragma unroll
+            for (int i = 0; i < MT / 16; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(cp) + i);
+#pragma unroll
+            for (int i = 0; i < MT / 16; ++i) {
+                const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const int m = i * 16 + j * 4 + bb;
+                        const uint32_t code = (ww[j] >> (8 * bb)) & 0xffu;
+                        lut_add<QT>(acc, lutS[m * ADC_K + code]);
+                    }
+            }
+        } else if constexpr (MT > 0 && MT % 4 == 0) {
+            uint32_t w[MT / 4];
+#pragma unroll
+            for (int i = 0; i < MT / 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(cp) + i);
+#pragma unroll
+            for (int i = 0; i < MT / 4; ++i)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const uint32_t code = (w[i] >> (8 * bb)) & 0xffu;
+                    lut_add<QT>(acc, lutS[(i * 4 + bb) * ADC_K + code]);
+                }
+        } else {
+            for (int m = 0; m < M; ++m) lut_add<QT>(acc, lutS[m * ADC_K + __ldg(cp + m)]);
+        }
+        if constexpr (FILTER) {
+#pragma unroll
+            for (int qq = 0; qq < QT; ++qq) {
+                if (qq < nqt && acc[qq] >= thr[qq]) {
+                    const unsigned int pos = atomicAdd(a.cnt + q0 + qq, 1u);
+                    if (pos < (unsigned int)a.cap)
+                        a.cand[(q0 + qq) * (int64_t)a.cap + pos] = pack_cand(acc[qq], (uint32_t)doc);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int qq = 0; qq < QT; ++qq)
+                if (qq < nqt) a.out[(q0 + qq) * a.ld_out + p] = acc[qq];
+        }
+    }
+}
+
+static int scan_qt(int M) {
+    const size_t per_q = (size_t)M * ADC_K * 4;
+    const size_t budget = 200 * 1024;
+    if (4 * per_q <= budget) return 4;
+    if (2 * per_q <= budget) return 2;
+    if (per_q <= 220 * 1024) return 1;
+    return 0;
+}
+
+template <int QT, int MT, bool FILTER>
+static int launch_scan_inst(const ScanArgs& a, int splits, cudaStream_t st) {
+    auto kern = adc_scan_kernel<QT, MT, FILTER>;
+    const size_t smem = (size_t)a.M * ADC_K * 4 * QT;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((a.nq + QT - 1) / QT), (unsigned)splits);
+    kern<<<grid, SCAN_THREADS, smem, st>>>(a);
+    RC_CHECK_LAUNCH("adc_scan_kernel");
+    return RC_OK;
+}
+
+template <bool FILTER>
+static int launch_scan(ScanArgs a, cudaStream_t st) {
+    if (a.nq <= 0 || a.npos <= 0) return RC_OK;
+    const int qt = scan_qt(a.M);
+    if (qt == 0) {
+        set_error("adc scan: M=%d too large for the shared-memory look-up table", a.M);
+        return RC_E_UNSUPPORTED;
+    }
+    // split the positions so that (a) the grid fills the machine and (b) one split's codes
+    // (<= ~8 MB) stay L2-resident while every query tile sweeps over them
+    const int64_t tiles = (a.nq + qt - 1) / qt;
+    int64_t pps = (8 << 20) / a.M;
+    const int64_t want = (4 * (int64_t)num_sms() + tiles - 1) / tiles;   // >= 4 CTAs per SM in total
+    if (want > 1) pps = std::min(pps, (a.npos + want - 1) / want);
+    pps = std::max<int64_t>(pps, SCAN_THREADS);
+    pps = (pps + SCAN_THREADS - 1) / SCAN_THREADS * SCAN_THREADS;
+    int64_t splits = (a.npos + pps - 1) / pps;
+    if (splits > 65535) {
+        pps = ((a.npos + 65534) / 65535 + SCAN_THREADS - 1) / SCAN_THREADS * SCAN_THREADS;
+        splits = (a.npos + pps - 1) / pps;
+    }
+    a.pos_per_split = pps;
+#define RC_SCAN(QT, MT) return launch_scan_inst<QT, MT, FILTER>(a, (int)splits, st)
+    if (qt == 4) {
+        switch (a.M) {
+            case 8: RC_SCAN(4, 8);
+            case 16: RC_SCAN(4, 16);
+            case 24: RC_SCAN(4, 24);
+            case 32: RC_SCAN(4, 32);
+            case 48: RC_SCAN(4, 48);
+            default: RC_SCAN(4, 0);
+        }
+    } else if (qt == 2) {
+        switch (a.M) {
+            case 64: RC_SCAN(2, 64);
+            case 96: RC_SCAN(2, 96);
+            default: RC_SCAN(2, 0);
+        }
+    }
+    RC_SCAN(1, 0);
+#undef RC_SCAN
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix select on dense score rows: key of the r-th largest score and #scores strictly above it
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+radix_select_kernel(const float* __restrict__ dense, int64_t ld, int64_t n, const int* __restrict__ rank_of_q,
+                    int rank_all, uint32_t* __restrict__ thr_key, float* __restrict__ thr_f,
+                    unsigned int* __restrict__ count_gt) {
+    __shared__ unsigned int hist[256];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ unsigned int s_remaining;
+    const int64_t q = blockIdx.x;
+    const float* row = dense + q * ld;
+    const unsigned int r = (unsigned int)(rank_of_q ? rank_of_q[q] : rank_all);  // 1-based from the top
+    if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = r; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, mask = s_mask;
+        for (int64_t i = threadIdx.x; i < n; i += SEL_THREADS) {
+            const uint32_t key = f32_to_key(row[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int rem = s_remaining, cum = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (cum + hist[b] >= rem) break;
+                cum += hist[b];
+            }
+            s_remaining = rem - cum;
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_mask = mask | (255u << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (thr_key) thr_key[q] = s_prefix;
+        if (thr_f) thr_f[q] = key_to_f32(s_prefix);
+        if (count_gt) count_gt[q] = r - s_remaining;
+    }
+}
+
+// exact gather of the top-k of a dense row into the candidate list: everything above the k-th key,
+// plus the (k - count_gt) smallest positions among the ties at the k-th key.
+__global__ void __launch_bounds__(SEL_THREADS)
+gather_topk_kernel(const float* __restrict__ dense, int64_t ld, int64_t n, int k, const uint32_t* __restrict__ thr_key,
+                   const unsigned int* __restrict__ count_gt, unsigned long long* __restrict__ cand, int cap,
+                   unsigned int* __restrict__ cnt) {
+    __shared__ unsigned int s_cnt;
+    __shared__ unsigned int warp_eq[SEL_THREADS / 32];
+    const int64_t q = blockIdx.x;
+    const float* row = dense + q * ld;
+    const uint32_t tk = thr_key[q];
+    const unsigned int need_eq = (unsigned int)k - count_gt[q];
+    unsigned long long* out = cand + q * (int64_t)cap;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned int eq_base = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += SEL_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        const bool in = i < n;
+        const float s = in ? row[i] : 0.0f;
+        const uint32_t key = f32_to_key(s);
+        if (in && key > tk) {
+            const unsigned int pos = atomicAdd(&s_cnt, 1u);
+            if (pos < (unsigned int)cap) out[pos] = pack_cand(s, (uint32_t)i);
+        }
+        if (eq_base < need_eq) {  // block-uniform
+            const bool is_eq = in && key == tk;
+            const unsigned int bal = __ballot_sync(0xffffffffu, is_eq);
+            if (lane == 0) warp_eq[warp] = __popc(bal);
+            __syncthreads();
+            unsigned int before = 0, total = 0;
+            for (int w = 0; w < SEL_THREADS / 32; ++w) {
+                const unsigned int c = warp_eq[w];
+                if (w < warp) before += c;
+                total += c;
+            }
+            if (is_eq) {
+                const unsigned int rank = eq_base + before + __popc(bal & ((1u << lane) - 1u));
+                if (rank < need_eq) {
+                    const unsigned int pos = atomicAdd(&s_cnt, 1u);
+                    if (pos < (unsigned int)cap) out[pos] = pack_cand(s, (uint32_t)i);
+                }
+            }
+            eq_base += total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[q] = s_cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-query bitonic sort of the candidate list, descending composite key; writes the top k
+// status[q] = 0 ok, 1 = too few candidates (< k_eff), 2 = candidate list overflowed
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+sort_candidates_kernel(const unsigned long long* __restrict__ cand, int cap, const unsigned int* __restrict__ cnt,
+                       int k, int k_eff, int64_t id_offset, float* __restrict__ scores, int64_t ld_s,
+                       int64_t* __restrict__ ids, int64_t ld_i, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned long long skeys[];
+    const int64_t q = blockIdx.x;
+    const unsigned int c = cnt[q];
+    if (c < (unsigned int)k_eff || c > (unsigned int)cap) {
+        if (threadIdx.x == 0) status[q] = c > (unsigned int)cap ? 2 : 1;
+        return;
+    }
+    int n = 2;
+    while (n < (int)c) n <<= 1;
+    const unsigned long long* src = cand + q * (int64_t)cap;
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) skeys[i] = i < (int)c ? src[i] : 0ull;
+    bitonic_sort_desc(skeys, n);
+    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+        if (i < k_eff) {
+            const unsigned long long key = skeys[i];
+            scores[q * ld_s + i] = key_to_f32((uint32_t)(key >> 32));
+            ids[q * ld_i + i] = id_offset + (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+        } else {
+            scores[q * ld_s + i] = -FLT_MAX;   // Faiss pads missing results with (lowest, -1)
+            ids[q * ld_i + i] = -1;
+        }
+    }
+    if (threadIdx.x == 0) status[q] = 0;
+}
+
+// merge W sorted lists per query: (W, nq, k) -> (nq, k).  ids must be in [0, 2^32) or -1 (padding).
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_merge_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_in, int W, int64_t nq, int k,
+                  int n_sort, float* __restrict__ scores, int64_t* __restrict__ ids) {
+    extern __shared__ __align__(16) unsigned long long skeys[];
+    const int64_t q = blockIdx.x;
+    for (int i = threadIdx.x; i < n_sort; i += SEL_THREADS) {
+        unsigned long long key = 0ull;
+        if (i < W * k) {
+            const int w = i / k, j = i - w * k;
+            const int64_t id = i_in[((int64_t)w * nq + q) * k + j];
+            if (id >= 0) key = pack_cand(s_in[((int64_t)w * nq + q) * k + j], (uint32_t)id);
+        }
+        skeys[i] = key;
+    }
+    bitonic_sort_desc(skeys, n_sort);
+    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+        const unsigned long long key = skeys[i];
+        if (key != 0ull) {
+            scores[q * k + i] = key_to_f32((uint32_t)(key >> 32));
+            ids[q * k + i] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+        } else {
+            scores[q * k + i] = -FLT_MAX;
+            ids[q * k + i] = -1;
+        }
+    }
+}
+
+__global__ void fill_pad_kernel(float* scores, int64_t* ids, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { scores[i] = -FLT_MAX; ids[i] = -1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host plan + orchestration
+// ---------------------------------------------------------------------------------------------
+struct AdcPlan {
+    bool dense_all;
+    int k_eff;
+    int64_t n_sample;     // sample positions (multiple of SAMPLE_BLK)
+    int64_t stride;       // distance between sample block starts
+    int rank_sample;      // rank of the threshold inside the sample
+    int64_t dense_floats; // size of the dense score buffer
+    int dense_rows;       // query rows per dense-all pass
+};
+
+static AdcPlan adc_plan(int64_t nq, int64_t N, int64_t k) {
+    AdcPlan p{};
+    p.k_eff = (int)std::min<int64_t>(k, N);
+    p.dense_all = N <= DENSE_N_MAX || p.k_eff > 2048;
+    const int64_t qc = std::min<int64_t>(nq, Q_CHUNK);
+    if (p.dense_all) {
+        // rows per pass bounded by ~1 GiB of scores
+        int64_t rows = std::max<int64_t>(FB_ROWS, std::min<int64_t>(qc, (1ll << 28) / std::max<int64_t>(N, 1)));
+        rows = (rows + 3) / 4 * 4;
+        p.dense_rows = (int)rows;
+        p.dense_floats = rows * N;
+        return p;
+    }
+    const int64_t target = std::min<int64_t>(CAND_CAP / 2, std::max<int64_t>(3 * (int64_t)p.k_eff, 2048));
+    int64_t ns = std::max<int64_t>(32768, (64 * N + target - 1) / target);
+    ns = (ns + SAMPLE_BLK - 1) / SAMPLE_BLK * SAMPLE_BLK;
+    const int64_t nblk = ns / SAMPLE_BLK;
+    p.n_sample = ns;
+    p.stride = N / nblk;                      // >= SAMPLE_BLK because N > DENSE_N_MAX >= 4 * ns is not
+    if (p.stride < SAMPLE_BLK) p.stride = SAMPLE_BLK;  // guaranteed; clamp keeps blocks disjoint
+    while (nblk * p.stride - (p.stride - SAMPLE_BLK) > N) --p.stride;  // last block must end inside N
+    p.rank_sample = (int)std::max<int64_t>(1, (target * ns + N - 1) / N);
+    p.dense_rows = FB_ROWS;
+    p.dense_floats = std::max<int64_t>(qc * ns, (int64_t)FB_ROWS * N);
+    return p;
+}
+
+struct AdcWs {
+    float* lut; float* dense; unsigned long long* cand; unsigned int* cnt; float* thr; uint32_t* thr_key;
+    unsigned int* count_gt; int* status; float* fb_lut; float* fb_scores; int64_t* fb_ids;
+};
+
+static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPlan& p, void* base, AdcWs* w) {
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off = align_up(off + n, 256);
+        return o;
+    };
+    const int64_t qc = std::max<int64_t>(std::min<int64_t>(nq, Q_CHUNK), FB_ROWS);
+    const size_t o_lut = take((size_t)qc * M * ADC_K * 4);
+    const size_t o_dense = take((size_t)p.dense_floats * 4);
+    const size_t o_cand = take((size_t)qc * CAND_CAP * 8);
+    const size_t o_cnt = take((size_t)qc * 4);
+    const size_t o_thr = take((size_t)qc * 4);
+    const size_t o_tk = take((size_t)qc * 4);
+    const size_t o_gt = take((size_t)qc * 4);
+    const size_t o_st = take((size_t)qc * 4);
+    const size_t o_fl = take((size_t)FB_ROWS * M * ADC_K * 4);
+    const size_t o_fs = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 4);
+    const size_t o_fi = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 8);
+    if (w) {
+        w->lut = (float*)(b + o_lut);
+        w->dense = (float*)(b + o_dense);
+        w->cand = (unsigned long long*)(b + o_cand);
+        w->cnt = (unsigned int*)(b + o_cnt);
+        w->thr = (float*)(b + o_thr);
+        w->thr_key = (uint32_t*)(b + o_tk);
+        w->count_gt = (unsigned int*)(b + o_gt);
+        w->status = (int*)(b + o_st);
+        w->fb_lut = (float*)(b + o_fl);
+        w->fb_scores = (float*)(b + o_fs);
+        w->fb_ids = (int64_t*)(b + o_fi);
+    }
+    return off;
+}
+
+static int launch_lut(const float* queries, int64_t ldq, const float* c, int64_t nq, int M, int ds, float* lut,
+                      cudaStream_t st) {
+    if (nq <= 0) return RC_OK;
+    for (int64_t q0 = 0; q0 < nq; q0 += 32768) {  // grid.x is fine up to 2^31, keep launches modest anyway
+        const int64_t n = std::min<int64_t>(32768, nq - q0);
+        dim3 grid((unsigned)n, (unsigned)M);
+        adc_lut_kernel<<<grid, ADC_K, (size_t)ds * 4, st>>>(queries + q0 * ldq, ldq, c, M, ds,
+                                                           lut + q0 * (int64_t)M * ADC_K);
+        RC_CHECK_LAUNCH("adc_lut_kernel");
+    }
+    return RC_OK;
+}
+
+static int sort_smem_attr() {
+    static bool done = false;
+    if (!done) {
+        RC_CUDA(cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
+        RC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
+        done = true;
+    }
+    return RC_OK;
+}
+
+// exact top-k of `rows` dense rows (each covering all N documents) into (scores, ids)
+static int dense_topk(const AdcWs& w, int rows, int64_t N, int k, int k_eff, int64_t id_offset, float* scores,
+                      int64_t ld_s, int64_t* ids, int64_t ld_i, cudaStream_t st) {
+    radix_select_kernel<<<rows, SEL_THREADS, 0, st>>>(w.dense, N, N, nullptr, k_eff, w.thr_key, nullptr, w.count_gt);
+    RC_CHECK_LAUNCH("radix_select_kernel");
+    gather_topk_kernel<<<rows, SEL_THREADS, 0, st>>>(w.dense, N, N, k_eff, w.thr_key, w.count_gt, w.cand, CAND_CAP,
+                                                     w.cnt);
+    RC_CHECK_LAUNCH("gather_topk_kernel");
+    sort_candidates_kernel<<<rows, SEL_THREADS, CAND_CAP * 8, st>>>(w.cand, CAND_CAP, w.cnt, k, k_eff, id_offset,
+                                                                   scores, ld_s, ids, ld_i, w.status);
+    RC_CHECK_LAUNCH("sort_candidates_kernel");
+    return RC_OK;
+}
+
+static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
+
+}  // namespace rc
+
+using namespace rc;
+
+RC_API void rc_adc_last_stats(int64_t out4[4]) {
+    for (int i = 0; i < 4; ++i) out4[i] = g_stats[i];
+}
+
+RC_API int rc_adc_lut(const float* queries, int64_t ldq, const float* centroids, int64_t nq, int M, int K, int ds,
+                      float* lut, void* stream) {
+    RC_REQUIRE(queries && centroids && lut, "rc_adc_lut: null pointer");
+    RC_REQUIRE(K == ADC_K, "rc_adc_lut: K must be 256 (8-bit codes), got %d", K);
+    RC_REQUIRE(nq >= 0 && M >= 1 && M <= 65535 && ds >= 1 && ldq >= (int64_t)M * ds, "rc_adc_lut: bad shape");
+    return launch_lut(queries, ldq, centroids, nq, M, ds, lut, (cudaStream_t)stream);
+}
+
+RC_API int rc_adc_scores(const float* lut, const uint8_t* codes, int64_t nq, int64_t n0, int64_t n, int M, float* out,
+                         void* stream) {
+    RC_REQUIRE(lut && codes && out, "rc_adc_scores: null pointer");
+    RC_REQUIRE(nq >= 0 && n0 >= 0 && n >= 0 && M >= 1, "rc_adc_scores: bad shape");
+    ScanArgs a{};
+    a.lut = lut; a.codes = codes; a.nq = nq; a.npos = n; a.blk = 0; a.stride = 0; a.n0 = n0; a.M = M;
+    a.out = out; a.ld_out = n;
+    return launch_scan<false>(a, (cudaStream_t)stream);
+}
+
+RC_API size_t rc_adc_search_workspace_bytes(int64_t nq, int64_t N, int M, int K, int64_t k) {
+    if (nq < 1 || N < 1 || M < 1 || k < 1 || K != ADC_K) return 256;
+    const AdcPlan p = adc_plan(nq, N, k);
+    return adc_ws_layout(nq, N, M, k, p, nullptr, nullptr) + 256;
+}
+
+RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroids, const uint8_t* codes, int64_t nq,
+                         int64_t N, int M, int K, int ds, int64_t k, int64_t id_offset, float* scores, int64_t* ids,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    RC_REQUIRE(K == ADC_K, "rc_adc_search: K must be 256 (8-bit codes), got %d", K);
+    RC_REQUIRE(nq >= 0 && N >= 0 && M >= 1 && ds >= 1 && k >= 1, "rc_adc_search: bad shape");
+    RC_REQUIRE(N < (1ll << 32), "rc_adc_search: N must be < 2^32 per shard");
+    if (nq == 0) return RC_OK;
+    RC_REQUIRE(queries && centroids && scores && ids, "rc_adc_search: null pointer");
+    RC_REQUIRE(ldq >= (int64_t)M * ds, "rc_adc_search: bad query stride");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 4; ++i) g_stats[i] = 0;
+    if (N == 0) {
+        const int64_t n = nq * k;
+        fill_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, ids, n);
+        RC_CHECK_LAUNCH("fill_pad_kernel");
+        return RC_OK;
+    }
+    RC_REQUIRE(codes && workspace, "rc_adc_search: null pointer");
+    RC_REQUIRE(((uintptr_t)workspace & 255) == 0, "rc_adc_search: workspace must be 256-byte aligned");
+    const AdcPlan p = adc_plan(nq, N, k);
+    if (p.k_eff > CAND_CAP) {
+        set_error("rc_adc_search: k=%lld > %d is not supported", (long long)k, CAND_CAP);
+        return RC_E_UNSUPPORTED;
+    }
+    if (scan_qt(M) == 0) {
+        set_error("rc_adc_search: M=%d too large", M);
+        return RC_E_UNSUPPORTED;
+    }
+    AdcWs w;
+    const size_t need = adc_ws_layout(nq, N, M, k, p, workspace, &w);
+    if (need > workspace_bytes) {
+        set_error("rc_adc_search: workspace %zu < %zu bytes", workspace_bytes, need);
+        return RC_E_WORKSPACE;
+    }
+    int rc = sort_smem_attr();
+    if (rc) return rc;
+    const int ik = (int)k;
+    g_stats[3] = p.dense_all ? 0 : p.n_sample;
+    std::vector<int> status_h;
+    std::vector<unsigned int> cnt_h;
+
+    for (int64_t c0 = 0; c0 < nq; c0 += Q_CHUNK) {
+        const int64_t qc = std::min<int64_t>(Q_CHUNK, nq - c0);
+        rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
+        if (rc) return rc;
+        if (p.dense_all) {
+            for (int64_t r0 = 0; r0 < qc; r0 += p.dense_rows) {
+                const int rows = (int)std::min<int64_t>(p.dense_rows, qc - r0);
+                ScanArgs a{};
+                a.lut = w.lut + r0 * (int64_t)M * ADC_K; a.codes = codes; a.nq = rows; a.npos = N; a.n0 = 0; a.M = M;
+                a.out = w.dense; a.ld_out = N;
+                rc = launch_scan<false>(a, st);
+                if (rc) return rc;
+                rc = dense_topk(w, rows, N, ik, p.k_eff, id_offset, scores + (c0 + r0) * k, k, ids + (c0 + r0) * k, k, st);
+                if (rc) return rc;
+            }
+            g_stats[1] += qc;
+            continue;
+        }
+        // 1. thresholds from a strided sample of the corpus
+        {
+            ScanArgs a{};
+            a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.blk = SAMPLE_BLK; a.stride = p.stride;
+            a.M = M; a.out = w.dense; a.ld_out = p.n_sample;
+            rc = launch_scan<false>(a, st);
+            if (rc) return rc;
+            radix_select_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(w.dense, p.n_sample, p.n_sample, nullptr,
+                                                                       p.rank_sample, nullptr, w.thr, nullptr);
+            RC_CHECK_LAUNCH("radix_select_kernel");
+        }
+        // 2. filtered scan of the whole corpus
+        RC_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)qc * 4, st));
+        {
+            ScanArgs a{};
+            a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = N; a.n0 = 0; a.M = M;
+            a.thr = w.thr; a.cnt = w.cnt; a.cand = w.cand; a.cap = CAND_CAP;
+            rc = launch_scan<true>(a, st);
+            if (rc) return rc;
+        }
+        // 3. per-query sort
+        sort_candidates_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
+            w.cand, CAND_CAP, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status);
+        RC_CHECK_LAUNCH("sort_candidates_kernel");
+        // 4. queries whose list under/overflowed take the exact dense path
+        status_h.resize(qc);
+        cnt_h.resize(qc);
+        RC_CUDA(cudaMemcpyAsync(status_h.data(), w.status, (size_t)qc * 4, cudaMemcpyDeviceToHost, st));
+        RC_CUDA(cudaMemcpyAsync(cnt_h.data(), w.cnt, (size_t)qc * 4, cudaMemcpyDeviceToHost, st));
+        RC_CUDA(cudaStreamSynchronize(st));
+        std::vector<int64_t> failed;
+        for (int64_t i = 0; i < qc; ++i) {
+            if (status_h[i] != 0) failed.push_back(i);
+            g_stats[2] = std::max<int64_t>(g_stats[2], cnt_h[i]);
+        }
+        g_stats[0] += qc - (int64_t)failed.size();
+        g_stats[1] += (int64_t)failed.size();
+        for (size_t f0 = 0; f0 < failed.size(); f0 += FB_ROWS) {
+            const int rows = (int)std::min<size_t>(FB_ROWS, failed.size() - f0);
+            for (int r = 0; r < rows; ++r)
+                RC_CUDA(cudaMemcpyAsync(w.fb_lut + (int64_t)r * M * ADC_K, w.lut + failed[f0 + r] * (int64_t)M * ADC_K,
+                                        (size_t)M * ADC_K * 4, cudaMemcpyDeviceToDevice, st));
+            ScanArgs a{};
+            a.lut = w.fb_lut; a.codes = codes; a.nq = rows; a.npos = N; a.n0 = 0; a.M = M;
+            a.out = w.dense; a.ld_out = N;
+            rc = launch_scan<false>(a, st);
+            if (rc) return rc;
+            rc = dense_topk(w, rows, N, ik, p.k_eff, id_offset, w.fb_scores, k, w.fb_ids, k, st);
+            if (rc) return rc;
+            for (int r = 0; r < rows; ++r) {
+                const int64_t q = c0 + failed[f0 + r];
+                RC_CUDA(cudaMemcpyAsync(scores + q * k, w.fb_scores + (int64_t)r * k, (size_t)k * 4,
+                                        cudaMemcpyDeviceToDevice, st));
+                RC_CUDA(cudaMemcpyAsync(ids + q * k, w.fb_ids + (int64_t)r * k, (size_t)k * 8,
+                                        cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    RC_CUDA(cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+RC_API int rc_topk_merge(const float* scores_in, const int64_t* ids_in, int W, int64_t nq, int64_t k, float* scores,
+                         int64_t* ids, void* stream) {
+    RC_REQUIRE(scores_in && ids_in && scores && ids, "rc_topk_merge: null pointer");
+    RC_REQUIRE(W >= 1 && nq >= 0 && k >= 1, "rc_topk_merge: bad shape");
+    if ((int64_t)W * k > CAND_CAP) {
+        set_error("rc_topk_merge: W*k = %lld > %d is not supported", (long long)W * k, CAND_CAP);
+        return RC_E_UNSUPPORTED;
+    }
+    if (nq == 0) return RC_OK;
+    int rc = sort_smem_attr();
+    if (rc) return rc;
+    int n_sort = 2;
+    while (n_sort < W * (int)k) n_sort <<= 1;
+    topk_merge_kernel<<<(unsigned)nq, SEL_THREADS, (size_t)n_sort * 8, (cudaStream_t)stream>>>(
+        scores_in, ids_in, W, nq, (int)k, n_sort, scores, ids);
+    RC_CHECK_LAUNCH("topk_merge_kernel");
+    return RC_OK;
+}

@@ -1,0 +1,197 @@
+// common.cuh -- shared helpers of librepconc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/repconc_b200.h"
+
+#define RC_API extern "C" __attribute__((visibility("default")))
+
+namespace rc {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return RC_E_CUDA;
+    }
+    return RC_OK;
+}
+
+#define RC_CHECK_LAUNCH(name)                                              \
+    do {                                                                   \
+        ::rc::count_launch();                                              \
+        int _rc = ::rc::check_cuda(cudaGetLastError(), name);              \
+        if (_rc != RC_OK) return _rc;                                      \
+    } while (0)
+
+#define RC_REQUIRE(cond, ...)                  \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::rc::set_error(__VA_ARGS__);      \
+            return RC_E_INVALID;               \
+        }                                      \
+    } while (0)
+
+#define RC_CUDA(call)                                         \
+    do {                                                      \
+        int _rc = ::rc::check_cuda((call), #call);            \
+        if (_rc != RC_OK) return _rc;                         \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;  // B200
+    }
+    return n;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// fp32 summation in the order of ATen's CPU sum kernel (inner contiguous reduction, 8-float
+// vectors, 4 independent accumulators, cascade of 4 levels).  The reference's distance table is
+// `((x - c)**2).sum(-1)` (modeling_repconc.py:50) on CPU tensors, so this order is what makes the
+// fp32 table -- and with it every argmin / centring decision -- bit-identical to the reference.
+// `f(j)` returns element j.  Explicit __fadd_rn: never contracted, never reassociated.
+// ---------------------------------------------------------------------------------------------
+
+// Compile-time length, n < 512 (no cascade level is ever completed below 512 elements).
+template <int N, typename F>
+__device__ __forceinline__ float sum_aten_order(F f) {
+    static_assert(N >= 1 && N < 512, "use sum_aten_order_rt");
+    if constexpr (N >= 8) {
+        constexpr int NV = N / 8;        // number of 8-float vectors
+        constexpr int NI = NV / 4;       // groups of 4 vectors (one per accumulator)
+        float acc[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) acc[k][l] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) acc[k][l] = __fadd_rn(acc[k][l], f((i * 4 + k) * 8 + l));
+#pragma unroll
+        for (int i = NI * 4; i < NV; ++i)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], f(i * 8 + l));
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], acc[k][l]);
+        float fin = 0.0f;
+#pragma unroll
+        for (int j = NV * 8; j < N; ++j) fin = __fadd_rn(fin, f(j));
+#pragma unroll
+        for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, acc[0][l]);
+        return fin;
+    } else {
+        constexpr int NI = N / 4;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = __fadd_rn(acc[k], f(i * 4 + k));
+#pragma unroll
+        for (int j = NI * 4; j < N; ++j) acc[0] = __fadd_rn(acc[0], f(j));
+#pragma unroll
+        for (int k = 1; k < 4; ++k) acc[0] = __fadd_rn(acc[0], acc[k]);
+        return acc[0];
+    }
+}
+
+// Run-time length (any n >= 1), including the cascade that starts at 512 elements.
+// W = 8 (vector items) when n >= 8, else 1.  Slow path: only used for unusual sub-vector sizes.
+template <typename F>
+__device__ float sum_aten_order_rt(F f, int n) {
+    const int W = n >= 8 ? 8 : 1;
+    const int nitems = n / W;
+    const int size = nitems / 4;
+    float acc[4][4][8];
+    for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 8; ++l) acc[j][k][l] = 0.0f;
+    int clog = 0;
+    if (size > 1) {
+        int x = size - 1;
+        while (x > 0) { x >>= 1; ++clog; }
+    }
+    const int level_power = (clog / 4) > 4 ? (clog / 4) : 4;
+    const int level_step = 1 << level_power;
+    const int level_mask = level_step - 1;
+    int i = 0;
+    while (i + level_step <= size) {
+        for (int j = 0; j < level_step; ++j, ++i)
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < W; ++l)
+                    acc[0][k][l] = __fadd_rn(acc[0][k][l], f((i * 4 + k) * W + l));
+        for (int j = 1; j < 4; ++j) {
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < W; ++l) {
+                    acc[j][k][l] = __fadd_rn(acc[j][k][l], acc[j - 1][k][l]);
+                    acc[j - 1][k][l] = 0.0f;
+                }
+            if ((i & (level_mask << (j * level_power))) != 0) break;
+        }
+    }
+    for (; i < size; ++i)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < W; ++l) acc[0][k][l] = __fadd_rn(acc[0][k][l], f((i * 4 + k) * W + l));
+    for (int j = 1; j < 4; ++j)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < W; ++l) acc[0][k][l] = __fadd_rn(acc[0][k][l], acc[j][k][l]);
+    for (int it = size * 4; it < nitems; ++it)
+        for (int l = 0; l < W; ++l) acc[0][0][l] = __fadd_rn(acc[0][0][l], f(it * W + l));
+    for (int k = 1; k < 4; ++k)
+        for (int l = 0; l < W; ++l) acc[0][0][l] = __fadd_rn(acc[0][0][l], acc[0][k][l]);
+    if (W == 1) return acc[0][0][0];
+    float fin = 0.0f;
+    for (int j = nitems * 8; j < n; ++j) fin = __fadd_rn(fin, f(j));
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, acc[0][0][l]);
+    return fin;
+}
+
+// (x - c)^2 in the reference's arithmetic: fp32 subtract, fp32 multiply, no contraction.
+__device__ __forceinline__ float sqdiff(float x, float c) {
+    const float d = __fsub_rn(x, c);
+    return __fmul_rn(d, d);
+}
+
+// warp reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// monotone float <-> uint32 mapping (larger float <=> larger key), NaN-free inputs
+__device__ __forceinline__ uint32_t f32_to_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_f32(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+}  // namespace rc

@@ -1,0 +1,141 @@
+"""B200-native drop-in for the PQ-index / search half of
+`repconc.models.repconc.evaluate_repconc` (evaluate_repconc.py:78-135,180-206).
+
+Same function names, argument meaning and return values as the reference; the index objects are
+the Faiss-free ones of `repconc_b200.faiss_compat`, the search is `rc_adc_search` (hand-written
+sm_100a kernels).  The HF-Trainer based encoders of the same reference file (`encode_corpus`,
+`encode_query`, `RepCONCEvaluater`) are callers of this path and stay in the reference.
+"""
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, faiss_compat as faiss, ops
+
+try:
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+
+def initialize_index(model):
+    """evaluate_repconc.py:78-86: empty IndexPQ(D, M, 8, IP) carrying the model's centroids."""
+    D, M = model.config.hidden_size, model.config.MCQ_M
+    assert model.config.MCQ_K == 256
+    index = faiss.IndexPQ(D, M, 8, faiss.METRIC_INNER_PRODUCT)
+    index.is_trained = True
+    # set centroid values
+    centroids = model.centroids.data.detach().cpu().numpy()
+    faiss.copy_array_to_vector(centroids.ravel(), index.pq.centroids)
+    return index
+
+
+def add_docs(index, new_codes: np.ndarray):
+    """evaluate_repconc.py:89-98: append (n, M) uint8 codes.  (The reference copies the whole code
+    vector on every call; here it is one amortised append.)"""
+    M = index.pq.code_size
+    new_n = len(new_codes)
+    assert new_codes.shape == (new_n, M)
+    index.add_codes(new_codes)
+
+
+def from_pq_to_ivfpq(indexpq):
+    """evaluate_repconc.py:101-118: view the PQ index as a one-list IVFPQ.  With nlist = 1 and a zero
+    coarse centroid the IVFPQ inner-product search is the plain PQ scan, so this shares the data."""
+    ivfpq = faiss.IndexIVFPQ(indexpq.pq.d, indexpq.pq.M, indexpq.pq.nbits, indexpq.metric_type)
+    ivfpq.pq = indexpq.pq
+    ivfpq.is_trained = True
+    ivfpq.codes = indexpq.codes
+    ivfpq.ntotal = indexpq.ntotal
+    return ivfpq
+
+
+def load_index_to_gpu(index, single_gpu_id: Optional[int] = None):
+    """evaluate_repconc.py:121-135: make the index device-resident (one H2D copy of N*M bytes).
+    One process drives one GPU here: without `single_gpu_id` the current CUDA device is used.
+    For the multi-GPU corpus-sharded search see `load_index_shard_to_gpu`."""
+    if isinstance(index, faiss.GpuIndexPQ):
+        return index
+    device = torch.device("cuda", torch.cuda.current_device() if single_gpu_id is None else single_gpu_id)
+    return faiss.GpuIndexPQ.from_host(index, device)
+
+
+def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarray, index, topk: int):
+    """evaluate_repconc.py:180-185."""
+    topk_scores, topk_idx = index.search(query_embeds, topk)
+    topk_ids = np.vstack([corpus_ids[x] for x in topk_idx])
+    assert len(query_ids) == len(topk_scores) == len(topk_ids)
+    return topk_scores, topk_ids
+
+
+def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarray, index, topk: int,
+                 batch_size: int):
+    """evaluate_repconc.py:188-206."""
+    all_topk_scores, all_topk_ids = [], []
+    iterations = math.ceil(len(query_ids) / batch_size)
+    for query_id_iter, query_embeds_iter in tqdm(zip(
+        np.array_split(query_ids, iterations),
+        np.array_split(query_embeds, iterations),
+    ), total=iterations, desc="Batch search"):
+        topk_scores, topk_ids = search(query_id_iter, query_embeds_iter, corpus_ids, index, topk)
+        all_topk_scores.append(topk_scores)
+        all_topk_ids.append(topk_ids)
+    all_topk_scores = np.concatenate(all_topk_scores, axis=0)
+    all_topk_ids = np.concatenate(all_topk_ids, axis=0)
+    return all_topk_scores, all_topk_ids
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-GPU: corpus-sharded scan.  The reference only replicates the index
+# (`co.shard = False`, evaluate_repconc.py:131-134); sharding is what the 8-GPU config needs.
+# ----------------------------------------------------------------------------------------------
+def shard_bounds(ntotal: int, rank: int, world: int):
+    """contiguous, balanced row ranges: the first (ntotal % world) shards hold one extra row."""
+    base, extra = divmod(int(ntotal), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def load_index_shard_to_gpu(index, rank: Optional[int] = None, world: Optional[int] = None, device=None):
+    """This rank's shard of the corpus as a resident index whose ids are global row positions."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_bounds(index.ntotal, rank, world)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return faiss.GpuIndexPQ.from_host(index, device, lo, hi)
+
+
+def merge_shard_results(all_scores: torch.Tensor, all_ids: torch.Tensor):
+    """(W, nq, k) per-shard sorted lists -> (nq, k) global top-k (score desc, id asc), on the GPU."""
+    lib = _lib.load()
+    ops._require_cuda(all_scores, "all_scores")
+    W, nq, k = all_scores.shape
+    all_scores = all_scores.float().contiguous()
+    all_ids = all_ids.long().contiguous()
+    with torch.cuda.device(all_scores.device):
+        scores = torch.empty((nq, k), dtype=torch.float32, device=all_scores.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=all_scores.device)
+        _lib.check(lib.rc_topk_merge(all_scores.data_ptr(), all_ids.data_ptr(), W, nq, k, scores.data_ptr(),
+                                     ids.data_ptr(), ops._stream()), "rc_topk_merge")
+    return scores, ids
+
+
+def sharded_search(shard_index, query_embeds, topk: int, group=None):
+    """Every rank scans its own shard for ALL queries, then one all_gather of the (nq, k) lists and a
+    k-way merge on every rank.  No collective touches the scan itself.  Returns CUDA tensors."""
+    if not isinstance(query_embeds, torch.Tensor):
+        query_embeds = torch.from_numpy(np.ascontiguousarray(query_embeds, dtype=np.float32))
+    q = query_embeds.to(shard_index.device)
+    s, i = shard_index.search_tensor(q, topk)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return s, i
+    gs = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
+    gi = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+    dist.all_gather_into_tensor(gs, s, group=group)
+    dist.all_gather_into_tensor(gi, i, group=group)
+    return merge_shard_results(gs, gi)

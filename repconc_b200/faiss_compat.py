@@ -1,0 +1,274 @@
+"""Faiss-free stand-ins for the handful of Faiss objects the reference's PQ-search path touches
+(evaluate_repconc.py:78-135,180-206; run_repconc_eval.py:39-58,123-127; finetune_jpq.py:157-162,
+176,208-214; run_warmup.py:181-189).  A maintainer swaps `import faiss` for
+
+    from repconc_b200 import faiss_compat as faiss
+
+in those files; the index objects keep the attribute names the call sites use (`index.pq.M`,
+`index.pq.centroids`, `index.codes`, `index.ntotal`, `index.search(x, k)`), the search itself runs
+in librepconc_b200.so on the GPU (there is no CPU search path: `--cpu_search` also lands here).
+
+Only IndexPQ with nbits == 8 and METRIC_INNER_PRODUCT is modelled -- that is all the reference
+builds (evaluate_repconc.py:80-81).
+"""
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+
+# ----------------------------------------------------------------------------------------------
+# std::vector look-alikes (faiss.copy_array_to_vector / vector_to_array call sites)
+# ----------------------------------------------------------------------------------------------
+class _Vector:
+    dtype = np.uint8
+
+    def __init__(self, n=0):
+        self._a = np.zeros(n, dtype=self.dtype)
+        self._owner = None
+
+    def size(self):
+        return int(self._a.size)
+
+    def resize(self, n):
+        n = int(n)
+        if n != self._a.size:
+            new = np.zeros(n, dtype=self.dtype)
+            m = min(n, self._a.size)
+            new[:m] = self._a[:m]
+            self._a = new
+            self._touch()
+
+    def _touch(self):
+        if self._owner is not None:
+            self._owner._version += 1
+
+    def __len__(self):
+        return self.size()
+
+
+class FloatVector(_Vector):
+    dtype = np.float32
+
+
+class ByteVector(_Vector):
+    dtype = np.uint8
+
+
+def copy_array_to_vector(a, v):
+    a = np.ascontiguousarray(a).ravel()
+    if a.dtype != v.dtype:
+        raise TypeError(f"copy_array_to_vector: expected {np.dtype(v.dtype)}, got {a.dtype}")
+    v._a = a.copy()
+    v._touch()
+
+
+def vector_to_array(v):
+    return v._a.copy()
+
+
+def omp_set_num_threads(n):  # run_repconc_eval.py:149 -- no CPU threads are used by the search
+    return None
+
+
+def get_num_gpus():
+    return torch.cuda.device_count()
+
+
+# ----------------------------------------------------------------------------------------------
+# ProductQuantizer / IndexPQ
+# ----------------------------------------------------------------------------------------------
+class ProductQuantizer:
+    def __init__(self, d, M, nbits, owner=None):
+        if nbits != 8:
+            raise NotImplementedError("only 8-bit PQ codes (K = 256) are supported")
+        if d % M != 0:
+            raise ValueError(f"d={d} is not a multiple of M={M}")
+        self.d, self.M, self.nbits = int(d), int(M), int(nbits)
+        self.ksub = 1 << nbits
+        self.dsub = self.d // self.M
+        self.code_size = self.M
+        self.centroids = FloatVector(self.M * self.ksub * self.dsub)   # layout [m][k][dsub]
+        self.centroids._owner = owner
+
+    def centroid_array(self):
+        return self.centroids._a.reshape(self.M, self.ksub, self.dsub)
+
+
+class IndexPQ:
+    """faiss.IndexPQ(d, M, 8, METRIC_INNER_PRODUCT) as the reference uses it (evaluate_repconc.py:81)."""
+
+    def __init__(self, d, M, nbits=8, metric=METRIC_INNER_PRODUCT):
+        if metric != METRIC_INNER_PRODUCT:
+            raise NotImplementedError("only METRIC_INNER_PRODUCT is supported")
+        self._version = 0
+        self.d = int(d)
+        self.metric_type = metric
+        self.is_trained = False
+        self.ntotal = 0
+        self.pq = ProductQuantizer(d, M, nbits, owner=self)
+        self.codes = ByteVector(0)                                      # layout [n][m]
+        self.codes._owner = self
+        self._gpu = None
+        self._gpu_version = -1
+
+    def code_array(self):
+        return self.codes._a[: self.ntotal * self.pq.M].reshape(self.ntotal, self.pq.M)
+
+    def add_codes(self, new_codes):
+        """append (n, M) uint8 codes (what add_docs does through the Faiss vector API)."""
+        new_codes = np.ascontiguousarray(new_codes, dtype=np.uint8)
+        assert new_codes.ndim == 2 and new_codes.shape[1] == self.pq.M
+        self.codes._a = np.concatenate([self.codes._a[: self.ntotal * self.pq.M], new_codes.ravel()])
+        self.ntotal += len(new_codes)
+        self._version += 1
+
+    def _resident(self, device=None):
+        if self._gpu is None or self._gpu_version != self._version or self._gpu.ntotal != self.ntotal:
+            self._gpu = GpuIndexPQ.from_host(self, device)
+            self._gpu_version = self._version
+        return self._gpu
+
+    def search(self, x, k):
+        """Faiss `index.search(x, k)` -> (D, I).  Runs on the current CUDA device; the codes are
+        uploaded on first use and kept resident until the index is modified."""
+        return self._resident().search(x, k)
+
+
+class IndexIVFPQ(IndexPQ):
+    """What `from_pq_to_ivfpq` returns: the same PQ index seen as a one-list IVFPQ (nlist = 1, zero
+    coarse centroid, ids = arange) -- numerically the identical search (evaluate_repconc.py:101-118)."""
+    nlist = 1
+
+
+class GpuIndexPQ:
+    """Device-resident PQ index: codes (N, M) uint8 and centroids (M, 256, dsub) fp32 in HBM.
+    `search` accepts numpy arrays (returns numpy) or CUDA tensors (returns CUDA tensors, as
+    finetune_jpq.py:176 needs).  `set_centroids` refreshes the centroids in place -- the resident
+    replacement of JPQ's per-step `synchronize_model_index` re-clone (finetune_jpq.py:208-214)."""
+
+    def __init__(self, codes, centroids, id_offset=0):
+        ops._require_cuda(codes, "codes")
+        ops._require_cuda(centroids, "centroids")
+        assert codes.dtype == torch.uint8 and codes.dim() == 2 and codes.is_contiguous()
+        self.codes = codes
+        self.centroids = centroids.detach().float().contiguous()
+        self.M, self.ksub, self.dsub = self.centroids.shape
+        assert codes.shape[1] == self.M and self.ksub == 256
+        self.d = self.M * self.dsub
+        self.id_offset = int(id_offset)
+        self.metric_type = METRIC_INNER_PRODUCT
+        self.is_trained = True
+        self._ws = None
+        self.last_stats = None
+
+    @classmethod
+    def from_host(cls, index, device=None, lo=0, hi=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        hi = index.ntotal if hi is None else hi
+        codes = torch.from_numpy(np.ascontiguousarray(index.code_array()[lo:hi])).to(device)
+        cent = torch.from_numpy(index.pq.centroid_array().copy()).to(device)
+        return cls(codes, cent, id_offset=lo)
+
+    @property
+    def ntotal(self):
+        return int(self.codes.shape[0])
+
+    @property
+    def device(self):
+        return self.codes.device
+
+    def set_centroids(self, centroids):
+        with torch.no_grad():
+            self.centroids.copy_(centroids.detach().reshape(self.centroids.shape))
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def search_tensor(self, x, k):
+        """x (nq, d) CUDA fp32 -> (scores (nq,k) fp32, ids (nq,k) int64), both CUDA."""
+        lib = _lib.load()
+        x = ops._rows_f32(x, "query_embeds")
+        if x.device != self.device:
+            x = x.to(self.device)
+        if x.shape[1] != self.d:
+            raise ValueError(f"query width {x.shape[1]} != index dimension {self.d}")
+        nq, k = x.shape[0], int(k)
+        with torch.cuda.device(self.device):
+            scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            if nq == 0:
+                return scores, ids
+            nws = lib.rc_adc_search_workspace_bytes(nq, self.ntotal, self.M, 256, k)
+            ws = self._workspace(nws)
+            _lib.check(lib.rc_adc_search(x.data_ptr(), ops._ld(x), self.centroids.data_ptr(), self.codes.data_ptr(),
+                                         nq, self.ntotal, self.M, 256, self.dsub, k, self.id_offset,
+                                         scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         ops._stream()), "rc_adc_search")
+            st = (_lib.c_i64 * 4)()
+            lib.rc_adc_last_stats(st)
+            self.last_stats = dict(filtered=st[0], dense=st[1], max_candidates=st[2], sample=st[3])
+        return scores, ids
+
+    def search(self, x, k):
+        if isinstance(x, torch.Tensor):
+            if not x.is_cuda:
+                x = x.to(self.device)
+            return self.search_tensor(x, k)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        xt = torch.from_numpy(x).pin_memory().to(self.device, non_blocking=True) if x.size else \
+            torch.empty(x.shape, device=self.device)
+        s, i = self.search_tensor(xt, k)
+        return s.cpu().numpy(), i.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# Faiss index file (`faiss.write_index` / `read_index`) for IndexPQ: fourcc "IxPq"
+# (faiss/impl/index_write.cpp of the pinned 1.7.1: index header, ProductQuantizer, codes vector,
+#  search_type, encode_signs, polysemous_ht).  Faiss is absent in this image, so the layout is
+#  restated from its published source and NOT verified against a Faiss-written file.
+# ----------------------------------------------------------------------------------------------
+_FOURCC_IXPQ = struct.unpack("<I", b"IxPq")[0]
+
+
+def write_index(index, path):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", _FOURCC_IXPQ))
+        f.write(struct.pack("<iqqq", index.d, index.ntotal, 1 << 20, 1 << 20))
+        f.write(struct.pack("<?i", bool(index.is_trained), index.metric_type))
+        f.write(struct.pack("<QQQ", index.pq.d, index.pq.M, index.pq.nbits))
+        cent = np.ascontiguousarray(index.pq.centroids._a, dtype=np.float32)
+        f.write(struct.pack("<Q", cent.size))
+        f.write(cent.tobytes())
+        codes = np.ascontiguousarray(index.codes._a[: index.ntotal * index.pq.M], dtype=np.uint8)
+        f.write(struct.pack("<Q", codes.size))
+        f.write(codes.tobytes())
+        f.write(struct.pack("<i?i", 0, False, index.pq.nbits * index.pq.M + 1))  # ST_PQ, no signs, ht
+
+
+def read_index(path):
+    with open(path, "rb") as f:
+        (h,) = struct.unpack("<I", f.read(4))
+        if h != _FOURCC_IXPQ:
+            raise NotImplementedError(f"read_index: only IndexPQ ('IxPq') files are supported, got fourcc {h:#x}")
+        d, ntotal, _, _ = struct.unpack("<iqqq", f.read(28))
+        is_trained, metric = struct.unpack("<?i", f.read(5))
+        if metric > 1:
+            f.read(4)
+        pd, pM, pnbits = struct.unpack("<QQQ", f.read(24))
+        index = IndexPQ(pd, pM, pnbits, metric)
+        (n,) = struct.unpack("<Q", f.read(8))
+        copy_array_to_vector(np.frombuffer(f.read(4 * n), dtype=np.float32), index.pq.centroids)
+        (n,) = struct.unpack("<Q", f.read(8))
+        copy_array_to_vector(np.frombuffer(f.read(n), dtype=np.uint8), index.codes)
+        index.ntotal = ntotal
+        index.is_trained = is_trained
+        assert index.d == d and n == ntotal * pM
+    return index

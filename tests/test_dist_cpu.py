@@ -1,0 +1,134 @@
+"""world_size-2 `gloo` tests of the host-side multi-rank logic (no GPU):
+  * `constrained_assign_driver` -- where the three all-reduces of the reference go -- driven with an
+    emulated kernel set (numpy restatement of the kernels' contract, test-only) must reproduce the
+    codes the REFERENCE produced on 2 gloo ranks (golden `assign_dist2_ds16`);
+  * corpus shard bounds + top-k merge semantics (oracle merge) reproduce the unsharded search.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import golden_cases as GC  # noqa: E402
+
+
+class EmulatedAssignKernels:
+    """numpy stand-in for ops.CudaAssignKernels: same methods, same state semantics
+    (table/minmax, lu, lv, P) as csrc/assign.cu, built on the oracle's bit-exact fp32 table."""
+
+    def __init__(self, x, c):
+        from oracle import oracle as O
+        self.O = O
+        self.x, self.c = x, c
+        self.M, self.K, self.ds = c.shape
+        self.B = x.shape[0]
+
+    def table(self):
+        self.tab = self.O.dist_table(self.x, self.c)                     # (M,B,K) fp32
+        mx, mn = self.O.table_minmax(self.tab)
+        self.minmax = torch.from_numpy(np.stack([mx, mn]))
+        return self.minmax
+
+    def begin(self, eps):
+        mm = self.minmax.numpy()
+        self.tab = self.O.center_table(self.tab, mm[0], mm[1])           # centred in place
+        self.a = -self.tab.astype(np.float64) / eps                      # (M,B,K)
+        self.lu = np.zeros((self.M, self.K))
+        self.lv = np.zeros((self.M, self.B))
+        self.P = torch.from_numpy(np.exp(self.a).sum(1))                 # (M,K) row sums
+        return self.P
+
+    def _update(self):
+        self.lu = self.lu - np.log(self.K * self.P.numpy())
+
+    def step(self, eps, B_global):
+        self._update()
+        w = self.a + self.lu[:, None, :] + self.lv[:, :, None]
+        q = np.exp(w)
+        z = B_global * q.sum(2)                                          # (M,B)
+        self.lv = self.lv - np.log(z)
+        self.P = torch.from_numpy((q / z[:, :, None]).sum(1))
+        return self.P
+
+    def finish(self, eps, apply_rowsum, uint8=False, B_global=None):
+        if apply_rowsum and B_global == 1:          # single column: exact tie in the reference -> code 0
+            return torch.zeros((self.B, self.M), dtype=torch.int64)
+        if apply_rowsum:
+            self._update()
+        w = self.a + self.lu[:, None, :]
+        return torch.from_numpy(np.argmax(w, axis=2).T.copy())
+
+    def read_flags(self):
+        return 0
+
+
+def _worker(rank, world, port, case, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from repconc_b200.ops import constrained_assign_driver
+    x, c = GC.assign_inputs(case)
+    per = case["B"] // world
+    kern = EmulatedAssignKernels(x[rank * per:(rank + 1) * per], c)
+    codes = constrained_assign_driver(kern, case["eps"], case["iters"], distributed=True)
+    ret[rank] = codes.numpy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_driver_two_ranks_gloo_matches_reference_two_ranks():
+    case = GC.DIST_CASES["dist2_ds16"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "assign_dist2_ds16.npz"))
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, 29733, case, ret), nprocs=2, join=True)
+        codes = np.concatenate([ret[0], ret[1]], 0)
+    assert np.array_equal(codes, g["codes_conc"].astype(np.int64))
+
+
+def test_driver_single_rank_matches_golden():
+    from repconc_b200.ops import constrained_assign_driver
+    for name in ("ds16_b512", "ds12_b300", "ds5_k64", "b1"):
+        case = GC.ASSIGN_CASES[name]
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"assign_{name}.npz"))
+        x, c = GC.assign_inputs(case)
+        codes = constrained_assign_driver(EmulatedAssignKernels(x, c), case["eps"], case["iters"], False)
+        assert np.array_equal(codes.numpy(), g["codes_conc"].astype(np.int64)), name
+
+
+def _shard_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from repconc_b200.evaluate_repconc import shard_bounds
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    lo, hi = shard_bounds(len(codes), rank, world)
+    s, i = O.adc_search(q, c, codes[lo:hi], 20, id_offset=lo)          # stands in for the shard's GPU scan
+    gs = [torch.empty(s.shape, dtype=torch.float32) for _ in range(world)]
+    gi = [torch.empty(i.shape, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gs, torch.from_numpy(s))
+    dist.all_gather(gi, torch.from_numpy(i))
+    ms, mi = O.topk_merge(torch.stack(gs).numpy(), torch.stack(gi).numpy())
+    ret[rank] = (ms, mi)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_search_protocol_two_ranks_gloo():
+    from oracle import oracle as O
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_shard_worker, args=(2, 29734, ret), nprocs=2, join=True)
+        r0, r1 = ret[0], ret[1]
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    s, i = O.adc_search(q, c, codes, 20)
+    for ms, mi in (r0, r1):
+        assert np.array_equal(ms, s) and np.array_equal(mi, i)

@@ -1,0 +1,188 @@
+"""GPU parity of the PQ asymmetric-distance search against the oracle (Faiss IndexPQ semantics as the
+reference uses them) and the golden fixtures (reference decode + matmul).  The scan accumulates in
+fp32, m ascending, exactly like the oracle, so scores and ids are compared bit-exactly; against the
+fp64 decode+matmul anchor the tolerance is the north_star's 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_cases as GC
+from tests.conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _index(c, codes):
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    return GpuIndexPQ(_dev(codes), _dev(c))
+
+
+@pytest.mark.parametrize("name", list(GC.ADC_CASES))
+def test_search_matches_oracle_and_golden(name, oracle):
+    case = GC.ADC_CASES[name]
+    g = golden(name)
+    q, c, codes = GC.adc_inputs(case)
+    idx = _index(c, codes)
+    for k in case["ks"]:
+        s, i = idx.search(q, k)
+        os_, oi = oracle.adc_search(q, c, codes, k)
+        assert np.array_equal(s, os_) and np.array_equal(i, oi)
+        gs, gi = g[f"scores_k{k}"], g[f"ids_k{k}"].astype(np.int64)
+        np.testing.assert_allclose(s, gs, rtol=1e-4, atol=1e-4)
+        diff = i != gi
+        assert np.all(np.abs(s[diff] - gs[diff]) <= 1e-4 * np.abs(gs[diff]) + 1e-4) and diff.mean() < 0.01
+    # CUDA tensors in -> CUDA tensors out (finetune_jpq.py:176)
+    st, it = idx.search(_dev(q), 10)
+    assert st.is_cuda and it.is_cuda and it.dtype == torch.int64
+    assert np.array_equal(it.cpu().numpy(), oracle.adc_search(q, c, codes, 10)[1])
+
+
+def test_lut_and_dense_scores_bit_exact(oracle):
+    from repconc_b200 import _lib, ops
+    from oracle import oracle_np as ON
+    lib = _lib.load()
+    case = GC.ADC_CASES["adc_m48"]
+    q, c, codes = GC.adc_inputs(case)
+    qd, cd, kd = _dev(q), _dev(c), _dev(codes)
+    M, K, ds = c.shape
+    lut = torch.empty((len(q), M, K), device="cuda")
+    _lib.check(lib.rc_adc_lut(qd.data_ptr(), qd.stride(0), cd.data_ptr(), len(q), M, K, ds, lut.data_ptr(),
+                              ops._stream()), "lut")
+    assert np.array_equal(lut.cpu().numpy(), oracle.adc_lut(q, c))
+    n0, n = 100, 3001
+    out = torch.empty((len(q), n), device="cuda")
+    _lib.check(lib.rc_adc_scores(lut.data_ptr(), kd.data_ptr(), len(q), n0, n, M, out.data_ptr(), ops._stream()),
+               "scores")
+    assert np.array_equal(out.cpu().numpy()[:4], ON.adc_scores(q[:4], c, codes)[:, n0:n0 + n])
+
+
+@pytest.mark.parametrize("M,ds", [(8, 4), (12, 4), (32, 8), (64, 4), (96, 8), (7, 3)])
+def test_all_code_widths(oracle, M, ds):
+    r = np.random.default_rng(100 + M)
+    N, nq = 3000, 9
+    c = r.standard_normal((M, 256, ds), dtype=np.float32)
+    codes = r.integers(0, 256, size=(N, M), dtype=np.uint8)
+    q = r.standard_normal((nq, M * ds), dtype=np.float32)
+    s, i = _index(c, codes).search(q, 17)
+    os_, oi = oracle.adc_search(q, c, codes, 17)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi)
+
+
+def test_edge_cases(oracle):
+    case = dict(GC.ADC_CASES["adc_m8"], N=37, nq=3)
+    q, c, codes = GC.adc_inputs(case)
+    idx = _index(c, codes)
+    s, i = idx.search(q, 50)                                   # k > N pads like Faiss
+    os_, oi = oracle.adc_search(q, c, codes, 50)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi)
+    assert np.all(i[:, 37:] == -1) and np.all(s[:, 37:] == np.finfo(np.float32).min)
+    s0, i0 = idx.search(np.zeros((0, 128), np.float32), 5)     # no queries
+    assert s0.shape == (0, 5) and i0.shape == (0, 5)
+    # all documents identical: N-way exact tie -> ids ascending
+    codes2 = np.repeat(codes[:1], 5000, axis=0)
+    s2, i2 = _index(c, codes2).search(q, 100)
+    assert np.array_equal(i2, np.tile(np.arange(100), (3, 1)))
+    # id_offset (a corpus shard)
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    sh = GpuIndexPQ(_dev(codes[10:]), _dev(c), id_offset=10)
+    s3, i3 = sh.search(q, 5)
+    o3 = oracle.adc_search(q, c, codes[10:], 5, id_offset=10)
+    assert np.array_equal(s3, o3[0]) and np.array_equal(i3, o3[1])
+
+
+def test_filtered_scan_path_large_corpus(oracle):
+    """N above the dense-path limit: sampled thresholds + filtered scan + sort, exact vs the oracle;
+    includes duplicate documents (ties) and a skewed block of near-identical high scorers."""
+    r = np.random.default_rng(77)
+    M, ds, N, nq, k = 16, 4, 600_000, 24, 1000
+    c = r.standard_normal((M, 256, ds), dtype=np.float32)
+    codes = r.integers(0, 256, size=(N, M), dtype=np.uint8)
+    codes[N // 2: N // 2 + 300] = codes[7]                     # 300 exact duplicates of doc 7
+    q = r.standard_normal((nq, M * ds), dtype=np.float32)
+    idx = _index(c, codes)
+    s, i = idx.search(q, k)
+    assert idx.last_stats["sample"] > 0 and idx.last_stats["filtered"] > 0
+    os_, oi = oracle.adc_search(q, c, codes, k)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi)
+    s10, i10 = idx.search(q, 10)
+    assert np.array_equal(i10, oi[:, :10]) and np.array_equal(s10, os_[:, :10])
+
+
+def test_fallback_when_thresholds_fail(oracle):
+    """Adversarial corpus for the sampler: every high scorer sits outside the sampled blocks, or a
+    huge tie group overflows the candidate list -> those queries must take the exact fallback."""
+    r = np.random.default_rng(78)
+    M, ds, N, nq, k = 8, 4, 400_000, 6, 50
+    c = r.standard_normal((M, 256, ds), dtype=np.float32)
+    codes = r.integers(0, 256, size=(N, M), dtype=np.uint8)
+    codes[1000:21000] = codes[0]                               # 20k-way exact tie (> candidate capacity)
+    q = r.standard_normal((nq, M * ds), dtype=np.float32)
+    # make the tie group the top scorer for query 0
+    from oracle import oracle as O
+    lut = O.adc_lut(q[:1], c)[0]
+    codes[0] = lut.argmax(1).astype(np.uint8)
+    codes[1000:21000] = codes[0]
+    idx = _index(c, codes)
+    s, i = idx.search(q, k)
+    os_, oi = oracle.adc_search(q, c, codes, k)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi)
+    assert idx.last_stats["dense"] >= 1
+
+
+def test_reference_wrappers_and_mrr(oracle):
+    """initialize_index / add_docs / from_pq_to_ivfpq / load_index_to_gpu / batch_search end to end on a
+    synthetic eval set; MRR@10 identical to the oracle's run."""
+    from repconc_b200 import evaluate_repconc as E, ops
+    r = np.random.default_rng(5)
+    D, M, K, N, nq = 128, 8, 256, 20000, 200
+    ds = D // M
+    docs = r.standard_normal((N, D), dtype=np.float32)
+    c = np.ascontiguousarray(docs[:K].reshape(K, M, ds).transpose(1, 0, 2))
+    rel = r.integers(0, N, size=nq)
+    queries = docs[rel] + 0.5 * r.standard_normal((nq, D), dtype=np.float32)
+
+    class Cfg:
+        hidden_size, MCQ_M, MCQ_K = D, M, K
+
+    class Model:
+        config = Cfg()
+        centroids = torch.nn.Parameter(torch.from_numpy(c))
+
+    codes = ops.nn_assign(_dev(docs), _dev(c), uint8=True).cpu().numpy()
+    assert np.array_equal(codes, oracle.nn_assign(docs, c).astype(np.uint8))
+    index = E.initialize_index(Model())
+    E.add_docs(index, codes[:12000])
+    E.add_docs(index, codes[12000:])
+    assert index.ntotal == N
+    gpu = E.load_index_to_gpu(E.from_pq_to_ivfpq(index))
+    corpus_ids = np.arange(N)[::-1].copy()                     # arbitrary external ids
+    qids = np.arange(nq)
+    s, ids = E.batch_search(qids, queries, corpus_ids, gpu, topk=10, batch_size=64)
+    os_, oi = oracle.adc_search(queries, c, codes, 10)
+    assert np.array_equal(s, os_) and np.array_equal(ids, corpus_ids[oi])
+    mrr = oracle.mrr_at_k(ids, corpus_ids[rel], 10)
+    assert mrr == oracle.mrr_at_k(corpus_ids[oi], corpus_ids[rel], 10) and mrr > 0.3
+    # host-side IndexPQ.search (the --cpu_search call site) lands on the same kernels
+    s2, i2 = index.search(queries[:5], 10)
+    assert np.array_equal(i2, oi[:5])
+
+
+def test_shard_merge(oracle):
+    from repconc_b200 import evaluate_repconc as E
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    case = GC.ADC_CASES["adc_m8"]
+    q, c, codes = GC.adc_inputs(case)
+    W, k = 4, 100
+    ss, ii = [], []
+    for w in range(W):
+        lo, hi = E.shard_bounds(len(codes), w, W)
+        s, i = GpuIndexPQ(_dev(codes[lo:hi]), _dev(c), id_offset=lo).search_tensor(_dev(q), k)
+        ss.append(s)
+        ii.append(i)
+    ms, mi = E.merge_shard_results(torch.stack(ss), torch.stack(ii))
+    os_, oi = oracle.adc_search(q, c, codes, k)
+    assert np.array_equal(ms.cpu().numpy(), os_) and np.array_equal(mi.cpu().numpy(), oi)
