@@ -34,6 +34,8 @@ extern "C" {
 /* flag bits written by the assign kernels into `flags` (one int32 on the device) */
 #define RC_FLAG_NONFINITE 1 /* Q would hold NaN/Inf: models/repconc/modeling_repconc.py:64-65 */
 #define RC_FLAG_AMPLITUDE 2 /* `assert torch.all(amplitude > 0)` would fire: modeling_repconc.py:83 */
+#define RC_FLAG_BADCODE 4   /* rc_decode saw a code outside [0, K) */
+#define RC_FLAG_SPARSE_UNSAFE 8 /* a row kept < 2^-12/K of mass: re-run with rc_sinkhorn_set_dense(1) */
 
 const char* rc_last_error(void);
 /* library / build identification: "repconc_b200 <version> sm_100a" */
@@ -91,13 +93,20 @@ int rc_dist_table(const float* x, int64_t ldx, const float* centroids, int64_t B
  * The all-reduces are the caller's (torch.distributed / NCCL on the same stream) -- the library
  * has no communicator.  iters == 0 is allowed (begin, finish).
  * ------------------------------------------------------------------------------------------- */
+/* Sinkhorn pass selection.  Default (0): for K == 256 the iteration passes evaluate only the table
+ * elements within 2^-72 of their column sum (the rest cannot change an fp64 sum; bound in
+ * csrc/assign.cu); 1: always the dense pass.  Env RC_SINKHORN_DENSE=1 sets the initial value.
+ * Returns the previous setting. */
+int rc_sinkhorn_set_dense(int dense);
 size_t rc_sinkhorn_state_bytes(int64_t B, int M, int K);
 /* device pointer to the (M,K) fp64 row-sum buffer inside `state` (the all-reduce operand) */
 double* rc_sinkhorn_rowsum_ptr(void* state, int64_t B, int M, int K);
 int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M, int K, double eps,
                       void* state, int32_t* flags, void* stream);
+/* step_index: 0 for the first step after rc_sinkhorn_begin, then 1, 2, ... (the first step always
+ * runs the dense pass: its input columns are not normalised yet) */
 int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
-                     void* state, int32_t* flags, void* stream);
+                     int step_index, void* state, int32_t* flags, void* stream);
 /* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0 */
 int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
@@ -169,6 +178,12 @@ int rc_topk_merge(const float* scores_in, const int64_t* ids_in, int W, int64_t 
 /* statistics of the last rc_adc_search on this thread: [0] queries served by the filtered scan,
  * [1] queries that took the exact dense fallback, [2] max candidates of any query, [3] sample size */
 void rc_adc_last_stats(int64_t out4[4]);
+/* measurement hooks: with timing enabled rc_adc_search brackets every filtered-scan launch (the
+ * dominant kernel) with CUDA events on `stream`; the sum of their durations (ms) and the number of
+ * launches of the last search on this thread are returned by the two getters */
+void rc_adc_enable_timing(int enable);
+double rc_adc_last_scan_ms(void);
+int rc_adc_last_scan_launches(void);
 
 #ifdef __cplusplus
 }

@@ -26,10 +26,11 @@ SIGNATURES = {
     "rc_nn_assign": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "rc_minmax_init": (c_int, [c_ptr, c_int, c_ptr]),
     "rc_dist_table": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_set_dense": (c_int, [c_int]),
     "rc_sinkhorn_state_bytes": (c_size, [c_i64, c_int, c_int]),
     "rc_sinkhorn_rowsum_ptr": (c_ptr, [c_ptr, c_i64, c_int, c_int]),
     "rc_sinkhorn_begin": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_f64, c_ptr, c_ptr, c_ptr]),
-    "rc_sinkhorn_step": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_step": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr]),
     "rc_sinkhorn_finish": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                    c_ptr]),
     "rc_decode": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
@@ -47,6 +48,9 @@ SIGNATURES = {
     "rc_adc_scores": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_ptr]),
     "rc_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "rc_adc_last_stats": (None, [ctypes.POINTER(c_i64)]),
+    "rc_adc_enable_timing": (None, [c_int]),
+    "rc_adc_last_scan_ms": (c_f64, []),
+    "rc_adc_last_scan_launches": (c_int, []),
 }
 
 

@@ -537,6 +537,11 @@ static int dense_topk(const AdcWs& w, int rows, int64_t N, int k, int k_eff, int
 
 static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
 
+// optional CUDA-event timing of the filtered corpus scan (the dominant kernel) inside rc_adc_search
+static int g_timing = 0;
+static thread_local double g_scan_ms = 0.0;
+static thread_local int g_scan_launches = 0;
+
 }  // namespace rc
 
 using namespace rc;
@@ -544,6 +549,10 @@ using namespace rc;
 RC_API void rc_adc_last_stats(int64_t out4[4]) {
     for (int i = 0; i < 4; ++i) out4[i] = g_stats[i];
 }
+
+RC_API void rc_adc_enable_timing(int enable) { g_timing = enable ? 1 : 0; }
+RC_API double rc_adc_last_scan_ms(void) { return g_scan_ms; }
+RC_API int rc_adc_last_scan_launches(void) { return g_scan_launches; }
 
 RC_API int rc_adc_lut(const float* queries, int64_t ldq, const float* centroids, int64_t nq, int M, int K, int ds,
                       float* lut, void* stream) {
@@ -609,6 +618,13 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
     g_stats[3] = p.dense_all ? 0 : p.n_sample;
     std::vector<int> status_h;
     std::vector<unsigned int> cnt_h;
+    g_scan_ms = 0.0;
+    g_scan_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_timing) {
+        RC_CUDA(cudaEventCreate(&ev0));
+        RC_CUDA(cudaEventCreate(&ev1));
+    }
 
     for (int64_t c0 = 0; c0 < nq; c0 += Q_CHUNK) {
         const int64_t qc = std::min<int64_t>(Q_CHUNK, nq - c0);
@@ -645,8 +661,10 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             ScanArgs a{};
             a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = N; a.n0 = 0; a.M = M;
             a.thr = w.thr; a.cnt = w.cnt; a.cand = w.cand; a.cap = CAND_CAP;
+            if (ev0) RC_CUDA(cudaEventRecord(ev0, st));
             rc = launch_scan<true>(a, st);
             if (rc) return rc;
+            if (ev1) RC_CUDA(cudaEventRecord(ev1, st));
         }
         // 3. per-query sort
         sort_candidates_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
@@ -658,6 +676,12 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         RC_CUDA(cudaMemcpyAsync(status_h.data(), w.status, (size_t)qc * 4, cudaMemcpyDeviceToHost, st));
         RC_CUDA(cudaMemcpyAsync(cnt_h.data(), w.cnt, (size_t)qc * 4, cudaMemcpyDeviceToHost, st));
         RC_CUDA(cudaStreamSynchronize(st));
+        if (ev0) {
+            float ms = 0.0f;
+            RC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            g_scan_ms += ms;
+            g_scan_launches += 1;
+        }
         std::vector<int64_t> failed;
         for (int64_t i = 0; i < qc; ++i) {
             if (status_h[i] != 0) failed.push_back(i);
@@ -687,6 +711,10 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         }
     }
     RC_CUDA(cudaStreamSynchronize(st));
+    if (ev0) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
     return RC_OK;
 }
 

@@ -15,6 +15,9 @@
 // accumulates the row sums that iteration t+1 needs.  Per iteration: 4 B/element of HBM traffic
 // instead of the reference's ~80 B/element, and ONE exp per element.
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "sinkhorn_math.cuh"
@@ -228,6 +231,36 @@ static int launch_table(const float* x, int64_t ldx, const float* c, int64_t B, 
 constexpr int SK_WARPS = 8;
 constexpr int SK_THREADS = SK_WARPS * 32;
 constexpr int SK_CTAS_PER_SM = 2;
+constexpr int SK_DEPTH = 4;  // table rows in flight per warp (TMA ring)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// one table row: global -> shared, 1-D bulk copy (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load_row(float* dst_smem, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 // Work partition: the (m, row-tile) space is flattened (m slow) and cut into G equal contiguous
 // ranges, one per persistent CTA -- balanced to one tile of SK_WARPS rows whatever M and B are.
@@ -240,11 +273,13 @@ struct SkPart {
 
 __host__ __device__ inline int64_t sk_lo(const SkPart& p, int g) { return (p.total * g) / p.G; }
 
-static SkPart sk_partition(int64_t B, int M) {
+constexpr int SK_MAX_CTAS_PER_SM = 4;  // partial buffer is sized for the largest grid any pass uses
+
+static SkPart sk_partition(int64_t B, int M, int ctas_per_sm = SK_CTAS_PER_SM) {
     SkPart p;
     p.tpm = (B + SK_WARPS - 1) / SK_WARPS;
     p.total = p.tpm * M;
-    p.G = num_sms() * SK_CTAS_PER_SM;
+    p.G = num_sms() * ctas_per_sm;
     const int64_t tpc = (p.total + p.G - 1) / p.G;
     p.S = (int)((tpc + p.tpm - 2) / p.tpm) + 1;
     if (p.S < 2) p.S = 2;
@@ -252,10 +287,11 @@ static SkPart sk_partition(int64_t B, int M) {
 }
 
 struct SkState {
-    double* lu;       // (M,K)
-    double* P;        // (M,K)
-    double* lv;       // (M,B)
-    double* partial;  // (G,S,K)
+    double* lu;       // (M,K)   log2 row scaling
+    double* P;        // (M,K)   row sums (all-reduce operand)
+    double* lv;       // (M,B)   log2 column scaling
+    double* partial;  // (G,S,K) per-CTA row-sum partials
+    double* cut;      // (M)     log2 significance threshold of the sparse pass
 };
 
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
@@ -269,8 +305,16 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
     const size_t o_lu = take((size_t)M * K * 8);
     const size_t o_P = take((size_t)M * K * 8);
     const size_t o_lv = take((size_t)M * (size_t)B * 8);
-    const size_t o_pa = take((size_t)p.G * p.S * K * 8);
+    size_t pa = 0;
+    for (int c = 1; c <= SK_MAX_CTAS_PER_SM; ++c) {
+        const SkPart pc = sk_partition(B, M, c);
+        pa = std::max(pa, (size_t)pc.G * pc.S * K * 8);
+    }
+    (void)p;
+    const size_t o_pa = take(pa);
+    const size_t o_cut = take((size_t)M * 8);
     if (s) {
+        s->cut = (double*)(b + o_cut);
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
         s->lv = (double*)(b + o_lv);
@@ -289,19 +333,40 @@ constexpr double SK_TIE_TOL_LOG2 = 0.0;
 
 // One pass over the table.  A warp owns one table row (= one column of Q) at a time; lane l holds
 // k = l, l+32, ... (KPL values, 128-byte coalesced loads).  The scaling vectors are in log2 units.
-template <int MODE, int KPL>
+// TMA = true: every table row (K*4 bytes, contiguous) is brought in by one cp.async.bulk into a per-warp
+// ring of SK_DEPTH shared-memory slots, completion on an mbarrier per slot -- SK_DEPTH rows in flight per
+// warp (the 4 warps per scheduler this register-heavy kernel runs at cannot cover HBM latency with
+// register prefetch alone).  TMA = false (K*4 not a multiple of 16): plain loads, one row ahead.
+template <int MODE, int KPL, bool TMA, bool FULL>
 __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
 sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax, int64_t B, double Bg, int M,
                      int K, double scale2 /* log2(e)/eps */, SkPart part, const double* __restrict__ lu_g,
                      double* __restrict__ lv_g, double* __restrict__ partial, int64_t* __restrict__ codes_mb,
                      uint8_t* __restrict__ codes_u8, int32_t* __restrict__ flags) {
-    __shared__ double red[SK_WARPS][KPL * 32];
+    // per-warp ring of SK_DEPTH rows (TMA) -- its first half doubles as the warp's slice of the CTA
+    // reduction buffer `red` once a segment's rows are consumed (SK_DEPTH * 4 >= 8 bytes per k)
+    static_assert(SK_DEPTH >= 2, "red[] aliases the ring");
+    __shared__ __align__(128) float ring[SK_WARPS * (TMA ? SK_DEPTH : 2) * KPL * 32];
+    __shared__ __align__(8) unsigned long long bars[TMA ? SK_WARPS * SK_DEPTH : 1];
+    constexpr int RING_W = (TMA ? SK_DEPTH : 2) * KPL * 32;  // floats per warp
+    auto red = [&](int w, int k) -> double& { return reinterpret_cast<double*>(ring + w * RING_W)[k]; };
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
     if (t_lo >= t_hi) return;
     const int m_first = (int)(t_lo / part.tpm);
     int bad = 0;
+    // per-warp ring state: `seq` counts rows consumed by this warp since kernel start
+    float* my_ring = ring + warp * RING_W;
+    const uint32_t my_bars = smem_u32(bars + (TMA ? warp * SK_DEPTH : 0));
+    const uint32_t row_bytes = (uint32_t)K * 4u;
+    uint32_t seq = 0;
+    if (TMA) {
+        if (lane == 0)
+            for (int d = 0; d < SK_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
+        fence_barrier_init();
+        __syncwarp();
+    }
 
     int64_t t = t_lo;
     while (t < t_hi) {
@@ -323,14 +388,24 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
             const int k = i * 32 + lane;
-            lu[i] = k < K ? (MODE != SK_BEGIN ? lu_g[(int64_t)m * K + k] : 0.0) : RC_PAD_LOG2;
+            lu[i] = (FULL || k < K) ? (MODE != SK_BEGIN ? lu_g[(int64_t)m * K + k] : 0.0) : RC_PAD_LOG2;
             acc[i] = 0.0;
         }
         float* tm = table + (int64_t)m * B * K;
         double* lvm = lv_g + (int64_t)m * B;
 
         float dv[KPL], nx[KPL];
-        if (nrows > 0) {
+        if (TMA) {
+            if (lane == 0) {
+                const int64_t pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
+                fence_proxy_async();
+                for (int64_t d = 0; d < pre; ++d) {
+                    const uint32_t slot = (seq + (uint32_t)d) % SK_DEPTH;
+                    bulk_load_row(my_ring + slot * KPL * 32, tm + (b_first + d * SK_WARPS) * K, row_bytes,
+                                  my_bars + 8 * slot);
+                }
+            }
+        } else if (nrows > 0) {
 #pragma unroll
             for (int i = 0; i < KPL; ++i) {
                 const int k = i * 32 + lane;
@@ -341,10 +416,21 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
         // 32 rows, so the log2 costs one evaluation per 32 rows instead of one per row
         double zk = 1.0, lvk = 0.0;
         int64_t bk = -1;
+        double lv_cur = 0.0, lv_nxt = 0.0;
+        if (MODE == SK_STEP) lv_nxt = lane < nrows ? lvm[b_first + (int64_t)lane * SK_WARPS] : 0.0;
         for (int64_t r = 0; r < nrows; ++r) {
             const int64_t b = b_first + r * SK_WARPS;
             float* row = tm + b * K;
-            if (r + 1 < nrows) {  // software prefetch of the next row
+            if (TMA) {
+                const uint32_t slot = seq % SK_DEPTH;
+                mbar_wait(my_bars + 8 * slot, (seq / SK_DEPTH) & 1u);
+                const float* src = my_ring + slot * KPL * 32;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    const int k = i * 32 + lane;
+                    dv[i] = (FULL || k < K) ? src[k] : 0.0f;
+                }
+            } else if (r + 1 < nrows) {  // software prefetch of the next row
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) {
                     const int k = i * 32 + lane;
@@ -358,20 +444,26 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
                 for (int i = 0; i < KPL; ++i) {
                     const int k = i * 32 + lane;
                     const float dc = __fdiv_rn(__fsub_rn(dv[i], middle), amplitude);
-                    if (k < K) row[k] = dc;
+                    if (FULL || k < K) row[k] = dc;
                     w[i] = fma(-(double)dc, scale2, lu[i]);
                     if (!(w[i] < 1024.0)) bad |= RC_FLAG_NONFINITE;      // exp overflow or NaN input
                 }
+                exp2_fast_batch<KPL, true>(w);
 #pragma unroll
-                for (int i = 0; i < KPL; ++i) acc[i] += exp2_fast(w[i]);
+                for (int i = 0; i < KPL; ++i) acc[i] += w[i];
                 if (lane == 0) lvm[b] = 0.0;
             } else if (MODE == SK_STEP) {
-                const double lvb = lvm[b];
+                // column scalings of a group of 32 rows are fetched together, one group ahead
+                if ((r & 31) == 0) {
+                    lv_cur = lv_nxt;
+                    const int64_t rn = r + 32 + lane;
+                    lv_nxt = rn < nrows ? lvm[b_first + rn * SK_WARPS] : 0.0;
+                }
+                const double lvb = __shfl_sync(0xffffffffu, lv_cur, (int)(r & 31));
                 double q[KPL];
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) q[i] = fma(-(double)dv[i], scale2, lu[i]) + lvb;
-#pragma unroll
-                for (int i = 0; i < KPL; ++i) q[i] = exp2_fast(q[i]);
+                exp2_fast_batch<KPL, false>(q);
                 double s = 0.0;
 #pragma unroll
                 for (int i = 0; i < KPL; ++i) s += q[i];
@@ -422,23 +514,205 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
                     if (codes_u8) codes_u8[b * M + m] = (uint8_t)bk2;
                 }
             }
+            if (TMA) {
+                // the slot's values have been consumed by the arithmetic above: refill it SK_DEPTH rows ahead
+                __syncwarp();
+                if (lane == 0 && r + SK_DEPTH < nrows) {
+                    const uint32_t slot = seq % SK_DEPTH;
+                    fence_proxy_async();
+                    bulk_load_row(my_ring + slot * KPL * 32, tm + (b + (int64_t)SK_DEPTH * SK_WARPS) * K, row_bytes,
+                                  my_bars + 8 * slot);
+                }
+                ++seq;
+            } else {
 #pragma unroll
-            for (int i = 0; i < KPL; ++i) dv[i] = nx[i];
+                for (int i = 0; i < KPL; ++i) dv[i] = nx[i];
+            }
         }
         if (MODE != SK_FINISH) {
             // deterministic CTA reduction of the row-sum partials: warp 0..7 in order
 #pragma unroll
-            for (int i = 0; i < KPL; ++i) red[warp][i * 32 + lane] = acc[i];
+            for (int i = 0; i < KPL; ++i) red(warp, i * 32 + lane) = acc[i];
             __syncthreads();
             double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * K;
             for (int k = threadIdx.x; k < K; k += SK_THREADS) {
-                double sum = red[0][k];
+                double sum = red(0, k);
 #pragma unroll
-                for (int w = 1; w < SK_WARPS; ++w) sum += red[w][k];
+                for (int w = 1; w < SK_WARPS; ++w) sum += red(w, k);
                 dst[k] = sum;
             }
             __syncthreads();
         }
+        t = t_end;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse STEP pass (K == 256).  At the reference's eps (0.003) a column of Q spans hundreds of log2
+// units: only ~10 % of a table row is within 2^-72 of its column sum (probed: 28 of 256 on synthetic
+// data, tools/../DESIGN.md), the rest cannot change an fp64 sum.  Per row the warp
+//   1. filters all 256 elements in fp32 (2 x LDS.128, FFMA, compare against the per-row threshold
+//      derived from `cut`, with 0.25 log2 units of slack for the fp32 rounding),
+//   2. compacts the survivors' k into a shared list (warp prefix sum),
+//   3. evaluates w = a + lu[k] + lv[b] and 2^w in fp64 for the survivors only, one per lane,
+//   4. finishes the column normalisation and adds Q/z to its private row-sum array in shared memory.
+// The accumulation order per (warp, k) is the row order, so the result is deterministic; the bound
+// on what is dropped is stated at sinkhorn_update_kernel.  The dense kernel above remains the path for
+// K != 256, for RC_SINKHORN_DENSE=1, and for the re-run when RC_FLAG_SPARSE_UNSAFE was raised.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_CTAS_PER_SM = 3;
+constexpr int SP_K = 256;
+constexpr int SP_OFF_ACC = SK_WARPS * SK_DEPTH * SP_K * 4;          // ring: 32 KB
+constexpr int SP_OFF_Q = SP_OFF_ACC + SK_WARPS * SP_K * 8;          // acc : 16 KB
+constexpr int SP_OFF_LU = SP_OFF_Q + SK_WARPS * SP_K * 8;           // q   : 16 KB
+constexpr int SP_OFF_KL = SP_OFF_LU + SP_K * 8;                     // lu  :  2 KB
+constexpr int SP_OFF_BAR = SP_OFF_KL + SK_WARPS * SP_K;             // k   :  2 KB
+constexpr int SP_SMEM = SP_OFF_BAR + SK_WARPS * SK_DEPTH * 8;
+
+__global__ void __launch_bounds__(SK_THREADS, SP_CTAS_PER_SM)
+sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double Bg, int M, double scale2,
+                            SkPart part, const double* __restrict__ lu_g, const double* __restrict__ cut_g,
+                            double* __restrict__ lv_g, double* __restrict__ partial, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char sp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* my_ring = reinterpret_cast<float*>(sp_smem) + warp * SK_DEPTH * SP_K;
+    double* acc_all = reinterpret_cast<double*>(sp_smem + SP_OFF_ACC);
+    double* my_acc = acc_all + warp * SP_K;
+    double* my_q = reinterpret_cast<double*>(sp_smem + SP_OFF_Q) + warp * SP_K;
+    double* lu_s = reinterpret_cast<double*>(sp_smem + SP_OFF_LU);
+    uint8_t* my_kl = sp_smem + SP_OFF_KL + warp * SP_K;
+    const uint32_t my_bars = smem_u32(sp_smem + SP_OFF_BAR) + warp * SK_DEPTH * 8;
+    const int g = blockIdx.x;
+    const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
+    if (t_lo >= t_hi) return;
+    const int m_first = (int)(t_lo / part.tpm);
+    int bad = 0;
+    uint32_t seq = 0;
+    if (lane == 0)
+        for (int d = 0; d < SK_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
+    fence_barrier_init();
+    __syncwarp();
+    const float scale32 = (float)scale2;
+    const uint32_t row_bytes = SP_K * 4u;
+
+    int64_t t = t_lo;
+    while (t < t_hi) {
+        const int m = (int)(t / part.tpm);
+        const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        const int64_t nrows = b_first < b_stop ? (b_stop - b_first + SK_WARPS - 1) / SK_WARPS : 0;
+        const float* tm = table + (int64_t)m * B * SP_K;
+        double* lvm = lv_g + (int64_t)m * B;
+
+        lu_s[threadIdx.x] = lu_g[(int64_t)m * SP_K + threadIdx.x];
+#pragma unroll
+        for (int i = 0; i < SP_K / 32; ++i) my_acc[i * 32 + lane] = 0.0;
+        __syncthreads();
+        // this lane's 8 columns: k = 4*lane + j (j < 4) and 128 + 4*lane + (j - 4)
+        float lu32[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lu32[j] = (float)lu_s[(j >> 2) * 128 + 4 * lane + (j & 3)];
+        const double cut_m = cut_g[m];
+
+        if (lane == 0) {
+            const int64_t pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
+            fence_proxy_async();
+            for (int64_t d = 0; d < pre; ++d) {
+                const uint32_t slot = (seq + (uint32_t)d) % SK_DEPTH;
+                bulk_load_row(my_ring + slot * SP_K, tm + (b_first + d * SK_WARPS) * SP_K, row_bytes, my_bars + 8 * slot);
+            }
+        }
+        double zk = 1.0, lvk = 0.0;
+        int64_t bk = -1;
+        double lv_cur = 0.0;
+        double lv_nxt = lane < nrows ? lvm[b_first + (int64_t)lane * SK_WARPS] : 0.0;
+        for (int64_t r = 0; r < nrows; ++r) {
+            const int64_t b = b_first + r * SK_WARPS;
+            if ((r & 31) == 0) {
+                lv_cur = lv_nxt;
+                const int64_t rn = r + 32 + lane;
+                lv_nxt = rn < nrows ? lvm[b_first + rn * SK_WARPS] : 0.0;
+            }
+            const double lvb = __shfl_sync(0xffffffffu, lv_cur, (int)(r & 31));
+            const uint32_t slot = seq % SK_DEPTH;
+            mbar_wait(my_bars + 8 * slot, (seq / SK_DEPTH) & 1u);
+            const float* src = my_ring + slot * SP_K;
+            // 1. fp32 filter
+            const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
+            const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
+            const float cutf = (float)(cut_m - lvb) - 0.25f;
+            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (!(fmaf(-dd[j], scale32, lu32[j]) < cutf)) mask |= 1u << j;   // NaN stays in (and is flagged)
+            // 2. compaction: exclusive prefix of the per-lane counts
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int pos = incl - cnt;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (mask & (1u << j)) my_kl[pos++] = (uint8_t)((j >> 2) * 128 + 4 * lane + (j & 3));
+            __syncwarp();
+            // 3. fp64 evaluation of the survivors
+            double s = 0.0, q0 = 0.0;
+            int k0 = 0;
+            for (int base = 0; base < total; base += 32) {
+                const int idx = base + lane;
+                const bool valid = idx < total;
+                const int k = valid ? my_kl[idx] : 0;
+                const double w = fma(-(double)src[k], scale2, lu_s[k]) + lvb;
+                if (!(w < 1024.0)) bad |= RC_FLAG_NONFINITE;
+                const double q = valid ? exp2_fast_estrin(w) : 0.0;
+                s += q;
+                if (base == 0) { q0 = q; k0 = k; }
+                else my_q[idx] = q;
+            }
+            s = warp_sum(s);
+            const double z = Bg * s;
+            const double rz = __drcp_rn(z);
+            // 4. row sums of the normalised column
+            if (lane < total) my_acc[k0] = fma(q0, rz, my_acc[k0]);
+            for (int base = 32; base < total; base += 32) {
+                const int idx = base + lane;
+                if (idx < total) {
+                    const int k = my_kl[idx];
+                    my_acc[k] = fma(my_q[idx], rz, my_acc[k]);
+                }
+            }
+            if (lane == (int)(r & 31)) { zk = z; lvk = lvb; bk = b; }
+            if ((r & 31) == 31 || r + 1 == nrows) {
+                if (bk >= 0) {
+                    if (!(zk > 0.0) || !isfinite(zk)) bad |= RC_FLAG_NONFINITE;
+                    lvm[bk] = lvk - log2(zk);
+                }
+                bk = -1;
+            }
+            __syncwarp();
+            if (lane == 0 && r + SK_DEPTH < nrows) {
+                fence_proxy_async();
+                bulk_load_row(my_ring + slot * SP_K, tm + (b + (int64_t)SK_DEPTH * SK_WARPS) * SP_K, row_bytes,
+                              my_bars + 8 * slot);
+            }
+            ++seq;
+        }
+        __syncthreads();
+        {
+            double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * SP_K;
+            double sum = acc_all[threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < SK_WARPS; ++w) sum += acc_all[w * SP_K + threadIdx.x];
+            dst[threadIdx.x] = sum;
+        }
+        __syncthreads();
         t = t_end;
     }
     if (bad) atomicOr(flags, bad);
@@ -449,9 +723,14 @@ __global__ void __launch_bounds__(256)
 sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, double* __restrict__ P) {
     const int m = blockIdx.x;
     const int64_t m_lo = (int64_t)m * part.tpm, m_hi = m_lo + part.tpm;
+    // only CTAs whose tile range [total*g/G, total*(g+1)/G) can touch [m_lo, m_hi)
+    int g_first = (int)((m_lo * part.G) / part.total) - 1;
+    int g_last = (int)((m_hi * part.G) / part.total) + 1;
+    if (g_first < 0) g_first = 0;
+    if (g_last > part.G - 1) g_last = part.G - 1;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         double sum = 0.0;
-        for (int g = 0; g < part.G; ++g) {
+        for (int g = g_first; g <= g_last; ++g) {
             const int64_t lo = sk_lo(part, g), hi = sk_lo(part, g + 1);
             if (lo >= hi || hi <= m_lo || lo >= m_hi) continue;
             const int slot = m - (int)(lo / part.tpm);
@@ -462,13 +741,39 @@ sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, d
 }
 
 // row normalisation in log2 form: lu[m,k] -= log2(K * P[m,k])     (Q /= sum_of_rows; Q /= K, :158-159)
-__global__ void sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, int64_t n, double Kd,
-                                       int32_t* __restrict__ flags) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double z = Kd * P[i];
-    if (!(z > 0.0) || !isfinite(z)) atomicOr(flags, RC_FLAG_NONFINITE);
-    lu[i] -= log2(z);
+// Also derives, per sub-vector, the significance threshold of the sparse pass that follows:
+// the previous column normalisation left every column of Q summing to exactly 1/B_global, this update
+// multiplies row k by 2^dlu[k], so every new column sum is >= 2^(min_k dlu) / B_global; an element with
+// log2 Q < cut = -log2(B_global) + min_k dlu - SK_MARGIN is below 2^-SK_MARGIN of its column sum.
+constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
+constexpr double SK_UNSAFE_LOG2 = -12.0; // a row that keeps < 2^-12 / K of mass voids the row-sum bound
+
+
+__global__ void __launch_bounds__(256)
+sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, int K, double Kd, double log2Bg,
+                       int check_mass, double* __restrict__ cut, int32_t* __restrict__ flags) {
+    __shared__ double red[8];
+    const int m = blockIdx.x;
+    double dmin = INFINITY;
+    int bad = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int64_t i = (int64_t)m * K + k;
+        const double z = Kd * P[i];
+        if (!(z > 0.0) || !isfinite(z)) bad |= RC_FLAG_NONFINITE;
+        const double dl = -log2(z);
+        if (check_mass && dl > -SK_UNSAFE_LOG2) bad |= RC_FLAG_SPARSE_UNSAFE;   // K*P[k] < 2^-12
+        lu[i] += dl;
+        dmin = fmin(dmin, dl);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dmin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) dmin = fmin(dmin, red[w]);
+        cut[m] = -log2Bg + dmin - SK_MARGIN;
+    }
+    if (bad) atomicOr(flags, bad);
 }
 
 __global__ void fill_f64_kernel(double* p, int64_t n, double v) {
@@ -482,14 +787,26 @@ static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, 
                        cudaStream_t st) {
     const double inv_eps = RC_LOG2E / eps;  // the passes work in base 2
     const int kpl = (K + 31) / 32;
-#define RC_SK_LAUNCH(KPL)                                                                                  \
-    sinkhorn_pass_kernel<MODE, KPL><<<p.G, SK_THREADS, 0, st>>>(table, minmax, B, Bg, M, K, inv_eps, p, s.lu, \
-                                                                s.lv, s.partial, mb, u8, flags)
+    const bool tma = (K % 4 == 0) && (((uintptr_t)table & 15) == 0);
+#define RC_SK_LAUNCH(KPL)                                                                                       \
+    do {                                                                                                        \
+        if (tma && K == KPL * 32)                                                                               \
+            sinkhorn_pass_kernel<MODE, KPL, true, true><<<p.G, SK_THREADS, 0, st>>>(                                \
+                table, minmax, B, Bg, M, K, inv_eps, p, s.lu, s.lv, s.partial, mb, u8, flags);                      \
+        else if (tma)                                                                                           \
+            sinkhorn_pass_kernel<MODE, KPL, true, false><<<p.G, SK_THREADS, 0, st>>>(                               \
+                table, minmax, B, Bg, M, K, inv_eps, p, s.lu, s.lv, s.partial, mb, u8, flags);                      \
+        else                                                                                                    \
+            sinkhorn_pass_kernel<MODE, KPL, false, false><<<p.G, SK_THREADS, 0, st>>>(                              \
+                table, minmax, B, Bg, M, K, inv_eps, p, s.lu, s.lv, s.partial, mb, u8, flags);                      \
+    } while (0)
     if (kpl <= 2) RC_SK_LAUNCH(2);
     else if (kpl <= 4) RC_SK_LAUNCH(4);
     else if (kpl <= 8) RC_SK_LAUNCH(8);
-    else if (kpl <= 16) RC_SK_LAUNCH(16);
-    else {
+    else if (kpl <= 16) {
+        sinkhorn_pass_kernel<MODE, 16, false, false><<<p.G, SK_THREADS, 0, st>>>(table, minmax, B, Bg, M, K, inv_eps, p, s.lu,
+                                                                         s.lv, s.partial, mb, u8, flags);
+    } else {
         set_error("sinkhorn: K=%d > 512 is not supported", K);
         return RC_E_UNSUPPORTED;
     }
@@ -504,16 +821,31 @@ static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaSt
     return RC_OK;
 }
 
-static int launch_update(const SkState& s, int M, int K, int32_t* flags, cudaStream_t st) {
-    const int64_t n = (int64_t)M * K;
-    sinkhorn_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, s.P, n, (double)K, flags);
+static int launch_update(const SkState& s, int M, int K, double Bg, int check_mass, int32_t* flags,
+                         cudaStream_t st) {
+    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, K, (double)K, log2(Bg), check_mass, s.cut, flags);
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
+}
+
+static int g_sinkhorn_dense = -1;  // -1: read RC_SINKHORN_DENSE from the environment on first use
+static bool sinkhorn_dense() {
+    if (g_sinkhorn_dense < 0) {
+        const char* e = getenv("RC_SINKHORN_DENSE");
+        g_sinkhorn_dense = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return g_sinkhorn_dense == 1;
 }
 
 }  // namespace rc
 
 using namespace rc;
+
+RC_API int rc_sinkhorn_set_dense(int dense) {
+    const int old = sinkhorn_dense() ? 1 : 0;
+    g_sinkhorn_dense = dense ? 1 : 0;
+    return old;
+}
 
 #define RC_DS_DISPATCH(ds, CALL, ...)     \
     switch (ds) {                         \
@@ -616,8 +948,8 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
     return launch_reduce(p, s, M, K, st);
 }
 
-RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps, void* state,
-                            int32_t* flags, void* stream) {
+RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
+                            int step_index, void* state, int32_t* flags, void* stream) {
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(B_global >= B, "rc_sinkhorn_step: B_global < B");
@@ -625,8 +957,25 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    rc = launch_update(s, M, K, flags, st);
+    // The sparse pass needs (a) columns that the previous STEP normalised to 1/B_global -- not true for
+    // the first STEP, which follows rc_sinkhorn_begin's unnormalised Q0 -- and (b) rows that kept their
+    // mass through that normalisation (checked by the update kernel from the second STEP on).
+    const bool sparse = step_index > 0 && K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
+    rc = launch_update(s, M, K, (double)B_global, sparse ? 1 : 0, flags, st);
     if (rc) return rc;
+    if (sparse) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SP_SMEM));
+            attr_done = true;
+        }
+        const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM);
+        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, (double)B_global, M, RC_LOG2E / eps,
+                                                                      ps, s.lu, s.cut, s.lv, s.partial, flags);
+        RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
+        return launch_reduce(ps, s, M, K, st);
+    }
     rc = launch_pass<SK_STEP>(const_cast<float*>(table), nullptr, B, (double)B_global, M, K, eps, p, s, nullptr,
                               nullptr, flags, st);
     if (rc) return rc;
@@ -652,7 +1001,7 @@ RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, i
         return RC_OK;
     }
     if (apply_rowsum) {
-        rc = launch_update(s, M, K, flags, st);
+        rc = launch_update(s, M, K, (double)B_global, 0, flags, st);
         if (rc) return rc;
     }
     return launch_pass<SK_FINISH>(const_cast<float*>(table), nullptr, B, (double)B, M, K, eps, p, s, codes_mb,

@@ -11,7 +11,7 @@
 
 namespace rc {
 
-constexpr int RC_FLAG_BADCODE = 4;
+
 
 __device__ __forceinline__ int64_t load_code(const int64_t* codes, int64_t sb, int64_t sm, const uint8_t* u8,
                                              int64_t b, int m, int M) {

@@ -39,6 +39,67 @@ __device__ __forceinline__ double exp2_fast(double w) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// N evaluations with the Horner recurrences interleaved coefficient by coefficient (N independent
+// dependency chains in flight: the fp64 pipe has ~16 cycles of latency and this kernel runs 4 warps per
+// scheduler).  CLAMP_HI = false when the caller guarantees w < 1024 (inside the iteration Q <= 1).
+template <int N, bool CLAMP_HI>
+__device__ __forceinline__ void exp2_fast_batch(double (&w)[N]) {
+    const double MAGIC = 6755399441055744.0;
+    int n[N];
+    double f[N], p[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double t = w[i] + MAGIC;
+        n[i] = __double2loint(t);
+        f[i] = w[i] - (t - MAGIC);
+        p[i] = fma(4.4558179083360645e-10, f[i], 7.074194297288521e-09);
+    }
+#define RC_HORNER(C)                                   \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) p[i] = fma(p[i], f[i], C);
+    RC_HORNER(1.0178057087733941e-07)
+    RC_HORNER(1.3215432535912375e-06)
+    RC_HORNER(1.5252733841556773e-05)
+    RC_HORNER(0.00015403530463724353)
+    RC_HORNER(0.001333355814640647)
+    RC_HORNER(0.009618129107587256)
+    RC_HORNER(0.055504108664821625)
+    RC_HORNER(0.24022650695910158)
+    RC_HORNER(0.6931471805599453)
+    RC_HORNER(1.0)
+#undef RC_HORNER
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int e = max(n[i], -1022);
+        if (CLAMP_HI) e = min(e, 1023);
+        w[i] = __hiloint2double(__double2hiint(p[i]) + (e << 20), __double2loint(p[i]));
+    }
+}
+
+// Latency-oriented single evaluation (Estrin's scheme: dependency depth 5 instead of 11) for the sparse
+// pass, where a lane evaluates ONE significant element per table row and the chain latency, not the
+// fp64 pipe, is what a row costs.  Same coefficients; w < 1024 guaranteed by the caller.
+__device__ __forceinline__ double exp2_fast_estrin(double w) {
+    const double MAGIC = 6755399441055744.0;
+    const double t = w + MAGIC;
+    const int n = max(__double2loint(t), -1022);
+    const double f = w - (t - MAGIC);
+    const double f2 = f * f;
+    const double p01 = fma(0.6931471805599453, f, 1.0);
+    const double p23 = fma(0.055504108664821625, f, 0.24022650695910158);
+    const double p45 = fma(0.001333355814640647, f, 0.009618129107587256);
+    const double p67 = fma(1.5252733841556773e-05, f, 0.00015403530463724353);
+    const double p89 = fma(1.0178057087733941e-07, f, 1.3215432535912375e-06);
+    const double pab = fma(4.4558179083360645e-10, f, 7.074194297288521e-09);
+    const double f4 = f2 * f2;
+    const double q0 = fma(p23, f2, p01);
+    const double q1 = fma(p67, f2, p45);
+    const double q2 = fma(pab, f2, p89);
+    const double f8 = f4 * f4;
+    const double r0 = fma(q1, f4, q0);
+    const double p = fma(q2, f8, r0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 constexpr double RC_LOG2E = 1.4426950408889634074;
 constexpr double RC_PAD_LOG2 = -4000.0;  // log2 scaling of padded (k >= K) lanes: 2^w clamps to ~0
 

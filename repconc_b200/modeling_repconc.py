@@ -175,10 +175,10 @@ def sinkhorn_algorithm(out: Tensor, epsilon: float, sinkhorn_iterations: int, us
         _identity_centring_check(minmax)
         ops._lib.check(lib.rc_sinkhorn_begin(table.data_ptr(), minmax.data_ptr(), B, M, K, float(epsilon), base,
                                              flags.data_ptr(), sp), "rc_sinkhorn_begin")
-        for _ in range(max(sinkhorn_iterations - 1, 0)):
+        for it in range(max(sinkhorn_iterations - 1, 0)):
             if use_distrib_train:
                 dist.all_reduce(P)
-            ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), base,
+            ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), it, base,
                                                 flags.data_ptr(), sp), "rc_sinkhorn_step")
         if use_distrib_train and sinkhorn_iterations >= 1:
             dist.all_reduce(P)

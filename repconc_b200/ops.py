@@ -17,6 +17,7 @@ logger = logging.getLogger(__name__)
 FLAG_NONFINITE = 1
 FLAG_AMPLITUDE = 2
 FLAG_BADCODE = 4
+FLAG_SPARSE_UNSAFE = 8
 
 
 def _stream():
@@ -134,6 +135,7 @@ class CudaAssignKernels:
         p = self.lib.rc_sinkhorn_rowsum_ptr(self.state.data_ptr(), self.B, self.M, self.K)
         off = p - self.state.data_ptr()
         self.P = self.state[off: off + self.M * self.K * 8].view(torch.float64).view(self.M, self.K)
+        self.nsteps = 0
         _lib.check(self.lib.rc_sinkhorn_begin(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, self.M, self.K,
                                               float(eps), self.state.data_ptr(), self.flags.data_ptr(), _stream()),
                    "rc_sinkhorn_begin")
@@ -141,8 +143,9 @@ class CudaAssignKernels:
 
     def step(self, eps, B_global):
         _lib.check(self.lib.rc_sinkhorn_step(self.tab.data_ptr(), self.B, int(B_global), self.M, self.K, float(eps),
-                                             self.state.data_ptr(), self.flags.data_ptr(), _stream()),
+                                             self.nsteps, self.state.data_ptr(), self.flags.data_ptr(), _stream()),
                    "rc_sinkhorn_step")
+        self.nsteps += 1
         return self.P
 
     def finish(self, eps, apply_rowsum, uint8=False, B_global=None):
@@ -161,8 +164,12 @@ class CudaAssignKernels:
     def read_flags(self):
         return int(self.flags.item())
 
+    def set_dense(self, dense):
+        """select the dense Sinkhorn pass (True) or the default sparse one; returns the previous setting"""
+        return bool(self.lib.rc_sinkhorn_set_dense(1 if dense else 0))
 
-def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=False):
+
+def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=False, _retry_dense=False):
     """Host sequence of RepCONC.quantize with use_constraint=True (modeling_repconc.py:53-66):
     which kernel runs when, and where the reference's three all-reduces go
       * MAX / MIN of the per-sub-vector extrema       (:78-80)
@@ -187,6 +194,15 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
         dist.all_reduce(P, dist.ReduceOp.SUM, group=group)
     codes = kern.finish(eps, iters >= 1, uint8=uint8, B_global=B_global)
     flags = kern.read_flags()
+    if flags & FLAG_SPARSE_UNSAFE and not _retry_dense:
+        # the sparse pass's error bound did not hold for this input (a centroid kept < 2^-12/K of mass):
+        # redo the whole assignment with the dense pass.  Every rank sees the same all-reduced row sums,
+        # so every rank takes this branch together.
+        prev = kern.set_dense(True)
+        try:
+            return constrained_assign_driver(kern, eps, iters, distributed, group, uint8, _retry_dense=True)
+        finally:
+            kern.set_dense(prev)
     if flags & FLAG_AMPLITUDE:
         raise AssertionError("amplitude > 0 (center_distance_for_constraint)")
     if flags & FLAG_NONFINITE:

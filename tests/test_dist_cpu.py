@@ -69,6 +69,9 @@ class EmulatedAssignKernels:
     def read_flags(self):
         return 0
 
+    def set_dense(self, dense):
+        return False
+
 
 def _worker(rank, world, port, case, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)

@@ -167,3 +167,42 @@ def test_sinkhorn_algorithm_function_matches_reference_q():
     np.testing.assert_allclose(Q.sum(2), g["q_rowsum"], rtol=1e-9)
     np.testing.assert_allclose(Q.transpose(0, 2, 1)[:, :2, :], g["q_head"], rtol=1e-9, atol=1e-300)
     assert abs(Q.sum(1) - 1).max() < 1e-12
+
+
+def test_sparse_and_dense_passes_agree():
+    """The default (sparse) Sinkhorn pass and the dense pass give identical codes and row sums that
+    agree to 1e-13 relative (the sparse pass drops only terms below 2^-64 of a column sum)."""
+    from repconc_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((2048, 768), generator=gen, device="cuda")
+    c = torch.randn((48, 256, 16), generator=gen, device="cuda")
+    out = {}
+    for dense in (False, True):
+        kern = ops.CudaAssignKernels(x, c)
+        prev = kern.set_dense(dense)
+        try:
+            kern.table()
+            P = kern.begin(0.003)
+            for _ in range(19):
+                P = kern.step(0.003, 2048)
+            out[dense] = (P.clone(), kern.finish(0.003, True).clone(), kern.read_flags())
+        finally:
+            kern.set_dense(prev)
+    assert out[False][2] == 0 and out[True][2] == 0
+    assert torch.equal(out[False][1], out[True][1])
+    rel = ((out[False][0] - out[True][0]).abs() / out[True][0]).max().item()
+    assert rel < 1e-13, rel
+
+
+def test_sparse_unsafe_flag_triggers_dense_rerun(oracle):
+    """A centroid far away from every point keeps almost no mass after the first column
+    normalisation: the sparse pass must flag it and the driver must re-run densely (same codes as
+    the oracle either way)."""
+    from repconc_b200 import ops
+    r = np.random.default_rng(3)
+    B, M, K, ds = 512, 2, 256, 8
+    x = r.standard_normal((B, M * ds), dtype=np.float32)
+    c = r.standard_normal((M, K, ds), dtype=np.float32)
+    c[:, 5, :] += 40.0                              # one outlier centroid per sub-vector
+    got = ops.constrained_assign(_dev(x), _dev(c), 0.003, 10, distributed=False).cpu().numpy()
+    assert np.array_equal(got, oracle.constrained_assign(x, c, 0.003, 10)["codes"])
