@@ -33,7 +33,7 @@ constexpr int ADC_K = 256;
 constexpr int SCAN_THREADS = 512;
 constexpr int SEL_THREADS = 1024;
 constexpr int CAND_CAP = 8192;        // candidate list capacity per query == max sortable k
-constexpr int Q_CHUNK = 1024;         // queries processed per pass of the host loop
+constexpr int Q_CHUNK = 2048;         // max queries processed per pass of the host loop
 constexpr int FB_ROWS = 4;            // exact-fallback queries per dense scan
 constexpr int64_t DENSE_N_MAX = 262144;  // corpora up to this size take the dense path
 constexpr int SAMPLE_BLK = 1024;      // sample = evenly spaced blocks of this many documents
@@ -170,6 +170,251 @@ adc_scan_kernel(ScanArgs a) {
                 if (qq < nqt) a.out[(q0 + qq) * a.ld_out + p] = acc[qq];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed integer filter scan.  The corpus scan is bound by shared-memory gather throughput (one
+// 16-byte gather per (document, sub-vector) per CTA pass; random codes -> ~2.4-way bank-group
+// conflicts), so the filter pass packs TWICE the queries into the same 16 bytes: each query's
+// table is quantised to unsigned integers  q = round((v - lo_m) / step) <= QMAX = 65535 / M  and two
+// queries share one 32-bit word; a plain 32-bit IADD then accumulates both (the 16-bit fields cannot
+// carry: M * QMAX <= 65535).  With |v - (lo_m + step*q)| <= step/2 a document whose exact fp32 score
+// reaches the threshold tau has  sum_m q  >=  (tau - sum_m lo_m) / step - M/2, so comparing the integer
+// sum against that bound (minus slack for the fp32 roundings) never loses a true top-k document.
+// Survivors are re-scored exactly (fp32, m ascending) by adc_rescore_sort_kernel, so the final scores
+// and ids are bit-identical to the unquantised scan.
+// ---------------------------------------------------------------------------------------------
+template <int QP> struct PackVec;   // QP = queries per entry
+template <> struct PackVec<2> { using type = uint32_t; };
+template <> struct PackVec<4> { using type = uint2; };
+template <> struct PackVec<8> { using type = uint4; };
+
+template <int QP>
+__device__ __forceinline__ void pack_add(uint32_t (&acc)[QP / 2], const typename PackVec<QP>::type& v);
+template <> __device__ __forceinline__ void pack_add<2>(uint32_t (&acc)[1], const uint32_t& v) { acc[0] += v; }
+template <> __device__ __forceinline__ void pack_add<4>(uint32_t (&acc)[2], const uint2& v) {
+    acc[0] += v.x; acc[1] += v.y;
+}
+template <> __device__ __forceinline__ void pack_add<8>(uint32_t (&acc)[4], const uint4& v) {
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+}
+
+// per query: lo[m] = min_k lut, step = max_m (max_k - min_k) / QMAX, qlut = round((v - lo) / step)
+// grid nq, block 256 (thread = k)
+__global__ void __launch_bounds__(256)
+adc_quantise_lut_kernel(const float* __restrict__ lut, int M, int qmax, uint16_t* __restrict__ qlut,
+                        float* __restrict__ step_out, double* __restrict__ sumlo_out,
+                        double* __restrict__ sumabs_out) {
+    extern __shared__ float q_lo[];   // M floats
+    __shared__ float red_lo[8], red_hi[8];
+    __shared__ float s_range;
+    const int64_t q = blockIdx.x;
+    const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+    const float* src = lut + q * (int64_t)M * ADC_K;
+    float range = 0.0f;
+    double sumabs = 0.0;
+    for (int m = 0; m < M; ++m) {
+        const float v = src[m * ADC_K + k];
+        const float lo = warp_min(v), hi = warp_max(v);
+        if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
+        __syncthreads();
+        if (k == 0) {
+            float l = red_lo[0], h = red_hi[0];
+            for (int w = 1; w < 8; ++w) { l = fminf(l, red_lo[w]); h = fmaxf(h, red_hi[w]); }
+            q_lo[m] = l;
+            range = fmaxf(range, h - l);
+            sumabs += (double)fmaxf(fabsf(l), fabsf(h));
+        }
+        __syncthreads();
+    }
+    if (k == 0) s_range = range;
+    __syncthreads();
+    // a degenerate (constant) table still needs a positive step
+    const float step = fmaxf(s_range, 1e-30f) / (float)qmax;
+    for (int m = 0; m < M; ++m) {
+        const float v = src[m * ADC_K + k];
+        int qi = __float2int_rn((v - q_lo[m]) / step);
+        qi = qi < 0 ? 0 : (qi > qmax ? qmax : qi);
+        qlut[(q * M + m) * ADC_K + k] = (uint16_t)qi;
+    }
+    if (k == 0) {
+        double s = 0.0;
+        for (int m = 0; m < M; ++m) s += (double)q_lo[m];
+        step_out[q] = step;
+        sumlo_out[q] = s;
+        sumabs_out[q] = sumabs;
+    }
+}
+
+// integer threshold of the packed scan from the exact fp32 threshold tau (see the bound above):
+// clamping in adc_quantise_lut_kernel only happens at the ends of the range, where it moves q towards
+// the exact value, so |v - (lo + step*q)| <= step * (0.5 + 1e-3) including the fp32 division rounding.
+__global__ void adc_int_threshold_kernel(const float* __restrict__ thr, const float* __restrict__ step,
+                                         const double* __restrict__ sumlo, const double* __restrict__ sumabs,
+                                         int M, int64_t nq, int* __restrict__ thr_i) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double t = ((double)thr[q] - sumlo[q]) / (double)step[q] - (double)M * 0.501 - 1.0;
+    // fp32 accumulation error of the exact score itself: <= M * 2^-24 * max|partial sum|, and every
+    // partial sum is bounded by sumabs = sum_m max_k |lut|; in units of step
+    const double slack = (double)M * 1.2e-7 * sumabs[q] / (double)step[q];
+    double ti = floor(t - slack);
+    if (!(ti > 0.0)) ti = 0.0;            // also catches NaN: everything passes, exact re-score decides
+    if (ti > 65535.0) ti = 65536.0;       // nothing can pass (cannot happen for a threshold taken from a sample)
+    thr_i[q] = (int)ti;
+}
+
+struct PackScanArgs {
+    const uint16_t* qlut;    // (nq, M, 256)
+    const uint8_t* codes;    // (N, M)
+    const int* thr_i;        // (nq)
+    int64_t nq, npos, pos_per_split;
+    int M;
+    unsigned int* cnt;       // (nq)
+    uint32_t* cand;          // (nq, cap) document positions
+    int cap;
+};
+
+template <int QP, int MT>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+adc_scan_packed_kernel(PackScanArgs a) {
+    using V = typename PackVec<QP>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* lutS = reinterpret_cast<V*>(smem_raw);  // [M][256], QP uint16 per entry
+    const int M = MT > 0 ? MT : a.M;
+    const int64_t q0 = (int64_t)blockIdx.x * QP;
+    const int nqt = (int)min((int64_t)QP, a.nq - q0);
+    {
+        uint16_t* lh = reinterpret_cast<uint16_t*>(smem_raw);
+        const int n = M * ADC_K;
+        for (int qq = 0; qq < QP; ++qq) {
+            const uint16_t* src = a.qlut + (q0 + qq) * (int64_t)n;
+            for (int i = threadIdx.x; i < n; i += SCAN_THREADS) lh[i * QP + qq] = qq < nqt ? src[i] : (uint16_t)0;
+        }
+    }
+    int thr[QP];
+#pragma unroll
+    for (int qq = 0; qq < QP; ++qq) thr[qq] = qq < nqt ? a.thr_i[q0 + qq] : 0x7fffffff;
+    __syncthreads();
+
+    const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
+    const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
+    for (int64_t p = p_lo + threadIdx.x; p < p_hi; p += SCAN_THREADS) {
+        const uint8_t* cp = a.codes + p * M;
+        uint32_t acc[QP / 2];
+#pragma unroll
+        for (int i = 0; i < QP / 2; ++i) acc[i] = 0u;
+        if constexpr (MT > 0 && MT % 16 == 0) {
+            uint4 w[MT / 16];
+#pragma unroll
+            for (int i = 0; i < MT / 16; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(cp) + i);
+#pragma unroll
+            for (int i = 0; i < MT / 16; ++i) {
+                const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const uint32_t code = (ww[j] >> (8 * bb)) & 0xffu;
+                        pack_add<QP>(acc, lutS[(i * 16 + j * 4 + bb) * ADC_K + code]);
+                    }
+            }
+        } else if constexpr (MT > 0 && MT % 4 == 0) {
+            uint32_t w[MT / 4];
+#pragma unroll
+            for (int i = 0; i < MT / 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(cp) + i);
+#pragma unroll
+            for (int i = 0; i < MT / 4; ++i)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const uint32_t code = (w[i] >> (8 * bb)) & 0xffu;
+                    pack_add<QP>(acc, lutS[(i * 4 + bb) * ADC_K + code]);
+                }
+        } else {
+            for (int m = 0; m < M; ++m) pack_add<QP>(acc, lutS[m * ADC_K + __ldg(cp + m)]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < QP; ++qq) {
+            const int s = (int)((acc[qq >> 1] >> (16 * (qq & 1))) & 0xffffu);
+            if (s >= thr[qq]) {
+                const unsigned int pos = atomicAdd(a.cnt + q0 + qq, 1u);
+                if (pos < (unsigned int)a.cap) a.cand[(q0 + qq) * (int64_t)a.cap + pos] = (uint32_t)p;
+            }
+        }
+    }
+}
+
+static int scan_qp(int M) {
+    const size_t per_q = (size_t)M * ADC_K * 2;
+    const size_t budget = 200 * 1024;
+    if (8 * per_q <= budget) return 8;
+    if (4 * per_q <= budget) return 4;
+    if (2 * per_q <= budget) return 2;
+    return 0;
+}
+
+template <int QP, int MT>
+static int launch_packed_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
+    auto kern = adc_scan_packed_kernel<QP, MT>;
+    const size_t smem = (size_t)a.M * ADC_K * 2 * QP;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((a.nq + QP - 1) / QP), (unsigned)splits);
+    kern<<<grid, SCAN_THREADS, smem, st>>>(a);
+    RC_CHECK_LAUNCH("adc_scan_packed_kernel");
+    return RC_OK;
+}
+
+static void scan_splits(int64_t nq, int qt, int64_t npos, int M, int64_t* pps_out, int64_t* splits_out) {
+    // split the positions so that (a) the grid fills the machine and (b) one split's codes (<= ~8 MB) stay
+    // L2-resident while every query tile sweeps over them
+    const int64_t tiles = (nq + qt - 1) / qt;
+    int64_t pps = (8 << 20) / M;
+    const int64_t want = (4 * (int64_t)num_sms() + tiles - 1) / tiles;   // >= 4 CTAs per SM in total
+    if (want > 1) pps = std::min(pps, (npos + want - 1) / want);
+    pps = std::max<int64_t>(pps, SCAN_THREADS);
+    pps = (pps + SCAN_THREADS - 1) / SCAN_THREADS * SCAN_THREADS;
+    int64_t splits = (npos + pps - 1) / pps;
+    if (splits > 65535) {
+        pps = ((npos + 65534) / 65535 + SCAN_THREADS - 1) / SCAN_THREADS * SCAN_THREADS;
+        splits = (npos + pps - 1) / pps;
+    }
+    *pps_out = pps;
+    *splits_out = splits;
+}
+
+static int launch_packed(PackScanArgs a, cudaStream_t st) {
+    if (a.nq <= 0 || a.npos <= 0) return RC_OK;
+    const int qp = scan_qp(a.M);
+    if (qp == 0) {
+        set_error("adc packed scan: M=%d too large", a.M);
+        return RC_E_UNSUPPORTED;
+    }
+    int64_t pps, splits;
+    scan_splits(a.nq, qp, a.npos, a.M, &pps, &splits);
+    a.pos_per_split = pps;
+#define RC_PSCAN(QP, MT) return launch_packed_inst<QP, MT>(a, (int)splits, st)
+    if (qp == 8) {
+        switch (a.M) {
+            case 8: RC_PSCAN(8, 8);
+            case 16: RC_PSCAN(8, 16);
+            case 24: RC_PSCAN(8, 24);
+            case 32: RC_PSCAN(8, 32);
+            case 48: RC_PSCAN(8, 48);
+            default: RC_PSCAN(8, 0);
+        }
+    } else if (qp == 4) {
+        switch (a.M) {
+            case 64: RC_PSCAN(4, 64);
+            case 96: RC_PSCAN(4, 96);
+            default: RC_PSCAN(4, 0);
+        }
+    }
+    RC_PSCAN(2, 0);
+#undef RC_PSCAN
 }
 
 static int scan_qt(int M) {
@@ -384,6 +629,71 @@ sort_candidates_kernel(const unsigned long long* __restrict__ cand, int cap, con
     if (threadIdx.x == 0) status[q] = 0;
 }
 
+// exact re-scoring of the packed scan's survivors + sort.  One CTA per query: every candidate document is
+// scored in fp32, m ascending, from the query's fp32 table (L2-resident), kept if it reaches the exact
+// threshold, then the survivors are sorted like sort_candidates_kernel does.
+// status: 0 ok, 1 fewer than k_eff exact survivors, 2 the approximate list overflowed, 3 too many survivors
+__global__ void __launch_bounds__(SEL_THREADS)
+adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict__ codes, int M,
+                        const float* __restrict__ thr, const uint32_t* __restrict__ cand, int cap,
+                        const unsigned int* __restrict__ cnt, int k, int k_eff, int64_t id_offset,
+                        float* __restrict__ scores, int64_t ld_s, int64_t* __restrict__ ids, int64_t ld_i,
+                        int* __restrict__ status, unsigned int* __restrict__ exact_cnt) {
+    extern __shared__ __align__(16) unsigned long long skeys[];
+    __shared__ unsigned int s_cnt;
+    const int64_t q = blockIdx.x;
+    const unsigned int c_approx = cnt[q];
+    if (c_approx > (unsigned int)cap) {
+        if (threadIdx.x == 0) { status[q] = 2; exact_cnt[q] = c_approx; }
+        return;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const float* t = lut + q * (int64_t)M * ADC_K;
+    const float tau = thr[q];
+    const uint32_t* src = cand + q * (int64_t)cap;
+    for (unsigned int i = threadIdx.x; i < c_approx; i += SEL_THREADS) {
+        const uint32_t doc = src[i];
+        const uint8_t* cp = codes + (int64_t)doc * M;
+        float sc = 0.0f;
+        if ((M & 3) == 0) {
+            for (int w = 0; w < M / 4; ++w) {
+                const uint32_t ww = __ldg(reinterpret_cast<const uint32_t*>(cp) + w);
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) sc += __ldg(t + (w * 4 + bb) * ADC_K + ((ww >> (8 * bb)) & 0xffu));
+            }
+        } else {
+            for (int m = 0; m < M; ++m) sc += __ldg(t + m * ADC_K + __ldg(cp + m));
+        }
+        if (sc >= tau) {
+            const unsigned int pos = atomicAdd(&s_cnt, 1u);
+            if (pos < (unsigned int)CAND_CAP) skeys[pos] = pack_cand(sc, doc);
+        }
+    }
+    __syncthreads();
+    const unsigned int c = s_cnt;
+    if (threadIdx.x == 0) exact_cnt[q] = c;
+    if (c < (unsigned int)k_eff || c > (unsigned int)CAND_CAP) {
+        if (threadIdx.x == 0) status[q] = c > (unsigned int)CAND_CAP ? 3 : 1;
+        return;
+    }
+    int n = 2;
+    while (n < (int)c) n <<= 1;
+    for (int i = (int)c + threadIdx.x; i < n; i += SEL_THREADS) skeys[i] = 0ull;
+    bitonic_sort_desc(skeys, n);
+    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+        if (i < k_eff) {
+            const unsigned long long key = skeys[i];
+            scores[q * ld_s + i] = key_to_f32((uint32_t)(key >> 32));
+            ids[q * ld_i + i] = id_offset + (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+        } else {
+            scores[q * ld_s + i] = -FLT_MAX;
+            ids[q * ld_i + i] = -1;
+        }
+    }
+    if (threadIdx.x == 0) status[q] = 0;
+}
+
 // merge W sorted lists per query: (W, nq, k) -> (nq, k).  ids must be in [0, 2^32) or -1 (padding).
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_merge_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_in, int W, int64_t nq, int k,
@@ -460,6 +770,8 @@ static AdcPlan adc_plan(int64_t nq, int64_t N, int64_t k) {
 struct AdcWs {
     float* lut; float* dense; unsigned long long* cand; unsigned int* cnt; float* thr; uint32_t* thr_key;
     unsigned int* count_gt; int* status; float* fb_lut; float* fb_scores; int64_t* fb_ids;
+    uint16_t* qlut; float* qstep; double* qsumlo; double* qsumabs; int* thr_i; uint32_t* cand32;
+    unsigned int* exact_cnt;
 };
 
 static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPlan& p, void* base, AdcWs* w) {
@@ -482,7 +794,21 @@ static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPl
     const size_t o_fl = take((size_t)FB_ROWS * M * ADC_K * 4);
     const size_t o_fs = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 4);
     const size_t o_fi = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 8);
+    const size_t o_ql = take((size_t)qc * M * ADC_K * 2);
+    const size_t o_qs = take((size_t)qc * 4);
+    const size_t o_qo = take((size_t)qc * 8);
+    const size_t o_qa = take((size_t)qc * 8);
+    const size_t o_ti = take((size_t)qc * 4);
+    const size_t o_c32 = take((size_t)qc * CAND_CAP * 4);
+    const size_t o_ec = take((size_t)qc * 4);
     if (w) {
+        w->qlut = (uint16_t*)(b + o_ql);
+        w->qstep = (float*)(b + o_qs);
+        w->qsumlo = (double*)(b + o_qo);
+        w->qsumabs = (double*)(b + o_qa);
+        w->thr_i = (int*)(b + o_ti);
+        w->cand32 = (uint32_t*)(b + o_c32);
+        w->exact_cnt = (unsigned int*)(b + o_ec);
         w->lut = (float*)(b + o_lut);
         w->dense = (float*)(b + o_dense);
         w->cand = (unsigned long long*)(b + o_cand);
@@ -515,6 +841,7 @@ static int sort_smem_attr() {
     static bool done = false;
     if (!done) {
         RC_CUDA(cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
+        RC_CUDA(cudaFuncSetAttribute(adc_rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
         RC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
         done = true;
     }
@@ -602,7 +929,7 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         set_error("rc_adc_search: k=%lld > %d is not supported", (long long)k, CAND_CAP);
         return RC_E_UNSUPPORTED;
     }
-    if (scan_qt(M) == 0) {
+    if (scan_qt(M) == 0 || scan_qp(M) == 0) {
         set_error("rc_adc_search: M=%d too large", M);
         return RC_E_UNSUPPORTED;
     }
@@ -626,8 +953,11 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         RC_CUDA(cudaEventCreate(&ev1));
     }
 
-    for (int64_t c0 = 0; c0 < nq; c0 += Q_CHUNK) {
-        const int64_t qc = std::min<int64_t>(Q_CHUNK, nq - c0);
+    // balanced chunks (a multiple of 8 queries: whole CTA tiles of the packed scan)
+    const int64_t n_chunks = (nq + Q_CHUNK - 1) / Q_CHUNK;
+    const int64_t chunk = std::min<int64_t>(Q_CHUNK, ((nq + n_chunks - 1) / n_chunks + 7) / 8 * 8);
+    for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
+        const int64_t qc = std::min<int64_t>(chunk, nq - c0);
         rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
         if (rc) return rc;
         if (p.dense_all) {
@@ -655,21 +985,29 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
                                                                        p.rank_sample, nullptr, w.thr, nullptr);
             RC_CHECK_LAUNCH("radix_select_kernel");
         }
-        // 2. filtered scan of the whole corpus
+        // 2. packed integer filter scan of the whole corpus (thresholds lowered by the quantisation bound)
         RC_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)qc * 4, st));
         {
-            ScanArgs a{};
-            a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = N; a.n0 = 0; a.M = M;
-            a.thr = w.thr; a.cnt = w.cnt; a.cand = w.cand; a.cap = CAND_CAP;
+            const int qmax = 65535 / M;
+            adc_quantise_lut_kernel<<<(unsigned)qc, ADC_K, (size_t)M * 4, st>>>(w.lut, M, qmax, w.qlut, w.qstep,
+                                                                              w.qsumlo, w.qsumabs);
+            RC_CHECK_LAUNCH("adc_quantise_lut_kernel");
+            adc_int_threshold_kernel<<<(unsigned)((qc + 255) / 256), 256, 0, st>>>(w.thr, w.qstep, w.qsumlo,
+                                                                                   w.qsumabs, M, qc, w.thr_i);
+            RC_CHECK_LAUNCH("adc_int_threshold_kernel");
+            PackScanArgs a{};
+            a.qlut = w.qlut; a.codes = codes; a.thr_i = w.thr_i; a.nq = qc; a.npos = N; a.M = M;
+            a.cnt = w.cnt; a.cand = w.cand32; a.cap = CAND_CAP;
             if (ev0) RC_CUDA(cudaEventRecord(ev0, st));
-            rc = launch_scan<true>(a, st);
+            rc = launch_packed(a, st);
             if (rc) return rc;
             if (ev1) RC_CUDA(cudaEventRecord(ev1, st));
         }
-        // 3. per-query sort
-        sort_candidates_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
-            w.cand, CAND_CAP, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status);
-        RC_CHECK_LAUNCH("sort_candidates_kernel");
+        // 3. exact re-score of the survivors + per-query sort
+        adc_rescore_sort_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
+            w.lut, codes, M, w.thr, w.cand32, CAND_CAP, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k,
+            ids + c0 * k, k, w.status, w.exact_cnt);
+        RC_CHECK_LAUNCH("adc_rescore_sort_kernel");
         // 4. queries whose list under/overflowed take the exact dense path
         status_h.resize(qc);
         cnt_h.resize(qc);
