@@ -250,13 +250,17 @@ def main():
     alg_per_launch = alg_per_query * (Ksteps * SEARCH_BATCH) / max(scan_launches, 1)
     scan_avg_s = scan_ms / 1e3 / max(scan_launches, 1)
     achieved = alg_per_launch / scan_avg_s / 1e9 if scan_avg_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "adc_scan_kernel<4,48,filter>", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+    # dram__bytes_read + dram__bytes_write of ONE launch (1200 queries x 8,841,823 docs) from the committed
+    # `ncu --set full` capture profiles/r01_adc_scan_packed_ncu.txt; scaled to this run's shard size
+    ncu_traffic = (523.925504e6 + 24.176896e6) * (n_shard / N_DOCS) if scan_launches == Ksteps else None
+    roofline = {"bound": "hbm", "kernel": "adc_scan_packed_kernel<8,48>", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": scan_avg_s * 1e3,
                 "share_of_step": scan_ms / adc_ms,
                 "note": "algorithmic bytes = every query streams every code byte once (SURVEY 8d); queries are "
-                        "tiled 4 per CTA so DRAM traffic is far below this and the fraction may exceed what a "
-                        "copy reaches -- the practical ceiling is shared-memory gather throughput"}
+                        "tiled 8 per CTA and a split's codes stay L2-resident, so DRAM traffic is ~500x below "
+                        "this; the kernel is bound by the shared-memory crossbar (ncu: LSU wavefronts 98.8% of "
+                        "peak, 2.5-way bank conflicts from random codes), not by HBM"}
 
     # ------------------------------------------------------------------ constrained assign (secondary)
     assign = None
@@ -292,7 +296,7 @@ def main():
         for i in range(W, W + Ksteps):
             x = xs_host[i].to(dev, non_blocking=True)
             c_, mse_ = assign_step(x)
-            c_host, mse_host = c_.cpu(), float(mse_)
+            c_host, mse_host = c_.cpu(), float(mse_.detach())
         barrier()
         as_e2e = Ksteps * ASSIGN_B * world / max_over_ranks(time.perf_counter() - t0)
         # the dominant kernel: one fused Sinkhorn iteration (row + column normalisation in one table pass)

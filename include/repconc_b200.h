@@ -107,6 +107,10 @@ int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M, int K
  * runs the dense pass: its input columns are not normalised yet) */
 int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                      int step_index, void* state, int32_t* flags, void* stream);
+/* the transport plan itself, Q (M,K,B) fp64 with columns summing to 1 -- what the reference's
+ * sinkhorn_algorithm returns (modeling_repconc.py:164-165); call instead of rc_sinkhorn_finish */
+int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
+                       int apply_rowsum, void* state, double* Q, int32_t* flags, void* stream);
 /* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0 */
 int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,

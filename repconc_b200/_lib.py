@@ -31,6 +31,7 @@ SIGNATURES = {
     "rc_sinkhorn_rowsum_ptr": (c_ptr, [c_ptr, c_i64, c_int, c_int]),
     "rc_sinkhorn_begin": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_f64, c_ptr, c_ptr, c_ptr]),
     "rc_sinkhorn_step": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_expand": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rc_sinkhorn_finish": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                    c_ptr]),
     "rc_decode": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),

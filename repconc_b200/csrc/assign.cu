@@ -550,17 +550,23 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 
 // ---------------------------------------------------------------------------------------------
 // Sparse STEP pass (K == 256).  At the reference's eps (0.003) a column of Q spans hundreds of log2
-// units: only ~10 % of a table row is within 2^-72 of its column sum (probed: 28 of 256 on synthetic
-// data, tools/../DESIGN.md), the rest cannot change an fp64 sum.  Per row the warp
-//   1. filters all 256 elements in fp32 (2 x LDS.128, FFMA, compare against the per-row threshold
-//      derived from `cut`, with 0.25 log2 units of slack for the fp32 rounding),
-//   2. compacts the survivors' k into a shared list (warp prefix sum),
-//   3. evaluates w = a + lu[k] + lv[b] and 2^w in fp64 for the survivors only, one per lane,
-//   4. finishes the column normalisation and adds Q/z to its private row-sum array in shared memory.
-// The accumulation order per (warp, k) is the row order, so the result is deterministic; the bound
-// on what is dropped is stated at sinkhorn_update_kernel.  The dense kernel above remains the path for
-// K != 256, for RC_SINKHORN_DENSE=1, and for the re-run when RC_FLAG_SPARSE_UNSAFE was raised.
+// units: only ~10 % of a table row lies within 2^-72 of the row's largest element (probed: 28 of 256
+// on synthetic data), and what lies below cannot change an fp64 column sum (dropped mass
+// <= 256 * 2^-72 = 2^-64 of the sum) nor -- as long as every centroid keeps a sane share of the mass,
+// which sinkhorn_update_kernel verifies (RC_FLAG_SPARSE_UNSAFE) -- an fp64 row sum.  Per row the warp
+//   1. evaluates log2 Q up to the column constant in fp32 for all 256 elements (2 x LDS.128 from the TMA
+//      ring, 8 FFMA) and takes the warp maximum,
+//   2. compacts the k of the elements within SK_MARGIN + 0.5 of that maximum (the 0.5 covers the fp32
+//      rounding, <= 2e-4) into a shared list by ballot / popc,
+//   3. evaluates those elements in fp64, one per lane: w = a + lu[k] - max, 2^w by Estrin's scheme,
+//   4. normalises by the column sum and adds Q / (B * sum) to the warp's private row-sum array.
+// The column scaling lv is not needed at all here: each column is normalised by its own sum, and the
+// row maximum keeps 2^w in range.  Accumulation order per (warp, k) is the row order -> deterministic.
+// The dense kernel above remains the path for K != 256, for RC_SINKHORN_DENSE=1 and for the re-run
+// after RC_FLAG_SPARSE_UNSAFE.
 // ---------------------------------------------------------------------------------------------
+constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
+constexpr double SK_UNSAFE_LOG2 = -8.0;  // a row that keeps < 2^-8 / K of mass voids the row-sum bound
 constexpr int SP_CTAS_PER_SM = 3;
 constexpr int SP_K = 256;
 constexpr int SP_OFF_ACC = SK_WARPS * SK_DEPTH * SP_K * 4;          // ring: 32 KB
@@ -571,9 +577,9 @@ constexpr int SP_OFF_BAR = SP_OFF_KL + SK_WARPS * SP_K;             // k   :  2 
 constexpr int SP_SMEM = SP_OFF_BAR + SK_WARPS * SK_DEPTH * 8;
 
 __global__ void __launch_bounds__(SK_THREADS, SP_CTAS_PER_SM)
-sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double Bg, int M, double scale2,
-                            SkPart part, const double* __restrict__ lu_g, const double* __restrict__ cut_g,
-                            double* __restrict__ lv_g, double* __restrict__ partial, int32_t* __restrict__ flags) {
+sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2,
+                            SkPart part, const double* __restrict__ lu_g, double* __restrict__ partial,
+                            int32_t* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char sp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* my_ring = reinterpret_cast<float*>(sp_smem) + warp * SK_DEPTH * SP_K;
@@ -595,6 +601,8 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double B
     __syncwarp();
     const float scale32 = (float)scale2;
     const uint32_t row_bytes = SP_K * 4u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float sel_margin = (float)SK_MARGIN + 0.5f;
 
     int64_t t = t_lo;
     while (t < t_hi) {
@@ -602,9 +610,8 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double B
         const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
         const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
         const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
-        const int64_t nrows = b_first < b_stop ? (b_stop - b_first + SK_WARPS - 1) / SK_WARPS : 0;
-        const float* tm = table + (int64_t)m * B * SP_K;
-        double* lvm = lv_g + (int64_t)m * B;
+        const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
+        const float* tm = table + ((int64_t)m * B + b_first) * SP_K;   // this warp's first row
 
         lu_s[threadIdx.x] = lu_g[(int64_t)m * SP_K + threadIdx.x];
 #pragma unroll
@@ -614,92 +621,78 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double B
         float lu32[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) lu32[j] = (float)lu_s[(j >> 2) * 128 + 4 * lane + (j & 3)];
-        const double cut_m = cut_g[m];
 
         if (lane == 0) {
-            const int64_t pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
+            const int pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
             fence_proxy_async();
-            for (int64_t d = 0; d < pre; ++d) {
+            for (int d = 0; d < pre; ++d) {
                 const uint32_t slot = (seq + (uint32_t)d) % SK_DEPTH;
-                bulk_load_row(my_ring + slot * SP_K, tm + (b_first + d * SK_WARPS) * SP_K, row_bytes, my_bars + 8 * slot);
+                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)d * SK_WARPS * SP_K, row_bytes, my_bars + 8 * slot);
             }
         }
-        double zk = 1.0, lvk = 0.0;
-        int64_t bk = -1;
-        double lv_cur = 0.0;
-        double lv_nxt = lane < nrows ? lvm[b_first + (int64_t)lane * SK_WARPS] : 0.0;
-        for (int64_t r = 0; r < nrows; ++r) {
-            const int64_t b = b_first + r * SK_WARPS;
-            if ((r & 31) == 0) {
-                lv_cur = lv_nxt;
-                const int64_t rn = r + 32 + lane;
-                lv_nxt = rn < nrows ? lvm[b_first + rn * SK_WARPS] : 0.0;
-            }
-            const double lvb = __shfl_sync(0xffffffffu, lv_cur, (int)(r & 31));
+        for (int r = 0; r < nrows; ++r) {
             const uint32_t slot = seq % SK_DEPTH;
             mbar_wait(my_bars + 8 * slot, (seq / SK_DEPTH) & 1u);
             const float* src = my_ring + slot * SP_K;
-            // 1. fp32 filter
+            // 1. fp32 log2 Q (up to the column constant) and its warp maximum
             const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
             const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
-            const float cutf = (float)(cut_m - lvb) - 0.25f;
-            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-            uint32_t mask = 0;
+            float wf[8];
+            wf[0] = fmaf(-d0.x, scale32, lu32[0]); wf[1] = fmaf(-d0.y, scale32, lu32[1]);
+            wf[2] = fmaf(-d0.z, scale32, lu32[2]); wf[3] = fmaf(-d0.w, scale32, lu32[3]);
+            wf[4] = fmaf(-d1.x, scale32, lu32[4]); wf[5] = fmaf(-d1.y, scale32, lu32[5]);
+            wf[6] = fmaf(-d1.z, scale32, lu32[6]); wf[7] = fmaf(-d1.w, scale32, lu32[7]);
+            float mx = fmaxf(fmaxf(fmaxf(wf[0], wf[1]), fmaxf(wf[2], wf[3])),
+                             fmaxf(fmaxf(wf[4], wf[5]), fmaxf(wf[6], wf[7])));
+            mx = warp_max(mx);
+            const float cutf = mx - sel_margin;
+            // 2. compaction by ballot
+            int base = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (!(fmaf(-dd[j], scale32, lu32[j]) < cutf)) mask |= 1u << j;   // NaN stays in (and is flagged)
-            // 2. compaction: exclusive prefix of the per-lane counts
-            const int cnt = __popc(mask);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+            for (int j = 0; j < 8; ++j) {
+                const bool keep = wf[j] >= cutf;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) my_kl[base + __popc(bal & lt_mask)] = (uint8_t)((j >> 2) * 128 + 4 * lane + (j & 3));
+                base += __popc(bal);
             }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            int pos = incl - cnt;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (mask & (1u << j)) my_kl[pos++] = (uint8_t)((j >> 2) * 128 + 4 * lane + (j & 3));
+            const int total = base;
             __syncwarp();
-            // 3. fp64 evaluation of the survivors
+            // 3. fp64 evaluation of the survivors, shifted by the row maximum
+            const double shift = (double)mx;
             double s = 0.0, q0 = 0.0;
             int k0 = 0;
-            for (int base = 0; base < total; base += 32) {
-                const int idx = base + lane;
+            {
+                const bool valid = lane < total;
+                k0 = valid ? my_kl[lane] : 0;
+                const double w = fma(-(double)src[k0], scale2, lu_s[k0]) - shift;
+                q0 = valid ? exp2_fast_estrin(w) : 0.0;
+                s = q0;
+            }
+            for (int bs = 32; bs < total; bs += 32) {
+                const int idx = bs + lane;
                 const bool valid = idx < total;
                 const int k = valid ? my_kl[idx] : 0;
-                const double w = fma(-(double)src[k], scale2, lu_s[k]) + lvb;
-                if (!(w < 1024.0)) bad |= RC_FLAG_NONFINITE;
+                const double w = fma(-(double)src[k], scale2, lu_s[k]) - shift;
                 const double q = valid ? exp2_fast_estrin(w) : 0.0;
                 s += q;
-                if (base == 0) { q0 = q; k0 = k; }
-                else my_q[idx] = q;
+                my_q[idx] = q;
             }
             s = warp_sum(s);
-            const double z = Bg * s;
-            const double rz = __drcp_rn(z);
-            // 4. row sums of the normalised column
+            if (!(s >= 0.5) || !isfinite(s)) bad |= RC_FLAG_NONFINITE;   // the maximum itself contributes ~1
+            // 4. Q / (B_global * column sum) into the row sums (:155, :162-163)
+            const double rz = __drcp_rn(s) * rBg;
             if (lane < total) my_acc[k0] = fma(q0, rz, my_acc[k0]);
-            for (int base = 32; base < total; base += 32) {
-                const int idx = base + lane;
+            for (int bs = 32; bs < total; bs += 32) {
+                const int idx = bs + lane;
                 if (idx < total) {
                     const int k = my_kl[idx];
                     my_acc[k] = fma(my_q[idx], rz, my_acc[k]);
                 }
             }
-            if (lane == (int)(r & 31)) { zk = z; lvk = lvb; bk = b; }
-            if ((r & 31) == 31 || r + 1 == nrows) {
-                if (bk >= 0) {
-                    if (!(zk > 0.0) || !isfinite(zk)) bad |= RC_FLAG_NONFINITE;
-                    lvm[bk] = lvk - log2(zk);
-                }
-                bk = -1;
-            }
             __syncwarp();
             if (lane == 0 && r + SK_DEPTH < nrows) {
                 fence_proxy_async();
-                bulk_load_row(my_ring + slot * SP_K, tm + (b + (int64_t)SK_DEPTH * SK_WARPS) * SP_K, row_bytes,
+                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
                               my_bars + 8 * slot);
             }
             ++seq;
@@ -745,8 +738,6 @@ sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, d
 // the previous column normalisation left every column of Q summing to exactly 1/B_global, this update
 // multiplies row k by 2^dlu[k], so every new column sum is >= 2^(min_k dlu) / B_global; an element with
 // log2 Q < cut = -log2(B_global) + min_k dlu - SK_MARGIN is below 2^-SK_MARGIN of its column sum.
-constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
-constexpr double SK_UNSAFE_LOG2 = -12.0; // a row that keeps < 2^-12 / K of mass voids the row-sum bound
 
 
 __global__ void __launch_bounds__(256)
@@ -761,7 +752,7 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, in
         const double z = Kd * P[i];
         if (!(z > 0.0) || !isfinite(z)) bad |= RC_FLAG_NONFINITE;
         const double dl = -log2(z);
-        if (check_mass && dl > -SK_UNSAFE_LOG2) bad |= RC_FLAG_SPARSE_UNSAFE;   // K*P[k] < 2^-12
+        if (check_mass && dl > -SK_UNSAFE_LOG2) bad |= RC_FLAG_SPARSE_UNSAFE;   // K*P[k] < 2^-8
         lu[i] += dl;
         dmin = fmin(dmin, dl);
     }
@@ -774,6 +765,29 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, in
         cut[m] = -log2Bg + dmin - SK_MARGIN;
     }
     if (bad) atomicOr(flags, bad);
+}
+
+// Transport plan Q (M,K,B) fp64 from the row scaling alone (API parity with sinkhorn_algorithm's return
+// value, modeling_repconc.py:164-165): Q[m,k,b] = 2^(a + lu[k]) / sum_k' 2^(a + lu[k']), columns sum to 1.
+// One warp per table row; not on the training path.
+__global__ void __launch_bounds__(256)
+sinkhorn_expand_kernel(const float* __restrict__ table, int64_t B, int M, int K, double scale2,
+                       const double* __restrict__ lu_g, double* __restrict__ Q) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.y;
+    const int64_t b = (int64_t)blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    const float* row = table + ((int64_t)m * B + b) * K;
+    const double* lu = lu_g + (int64_t)m * K;
+    double mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) mx = fmax(mx, fma(-(double)row[k], scale2, lu[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double s = 0.0;
+    for (int k = lane; k < K; k += 32) s += exp2(fma(-(double)row[k], scale2, lu[k]) - mx);
+    s = warp_sum(s);
+    for (int k = lane; k < K; k += 32)
+        Q[((int64_t)m * K + k) * B + b] = exp2(fma(-(double)row[k], scale2, lu[k]) - mx) / s;
 }
 
 __global__ void fill_f64_kernel(double* p, int64_t n, double v) {
@@ -957,11 +971,11 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    // The sparse pass needs (a) columns that the previous STEP normalised to 1/B_global -- not true for
-    // the first STEP, which follows rc_sinkhorn_begin's unnormalised Q0 -- and (b) rows that kept their
-    // mass through that normalisation (checked by the update kernel from the second STEP on).
-    const bool sparse = step_index > 0 && K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
-    rc = launch_update(s, M, K, (double)B_global, sparse ? 1 : 0, flags, st);
+    // The sparse pass needs rows (centroids) that kept their share of the mass through the previous column
+    // normalisation; the update kernel checks that from the second STEP on (the first update sees the row
+    // sums of the unnormalised Q0, which say nothing about it).
+    const bool sparse = K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
+    rc = launch_update(s, M, K, (double)B_global, (sparse && step_index > 0) ? 1 : 0, flags, st);
     if (rc) return rc;
     if (sparse) {
         static bool attr_done = false;
@@ -971,8 +985,8 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
             attr_done = true;
         }
         const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM);
-        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, (double)B_global, M, RC_LOG2E / eps,
-                                                                      ps, s.lu, s.cut, s.lv, s.partial, flags);
+        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, 1.0 / (double)B_global, M,
+                                                                      RC_LOG2E / eps, ps, s.lu, s.partial, flags);
         RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
         return launch_reduce(ps, s, M, K, st);
     }
@@ -980,6 +994,25 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
                               nullptr, flags, st);
     if (rc) return rc;
     return launch_reduce(p, s, M, K, st);
+}
+
+RC_API int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
+                              int apply_rowsum, void* state, double* Q, int32_t* flags, void* stream) {
+    int rc = sk_args(table, B, M, K, eps, state, flags);
+    if (rc) return rc;
+    RC_REQUIRE(Q, "rc_sinkhorn_expand: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const SkPart p = sk_partition(B, M);
+    SkState s;
+    sk_layout(B, M, K, p, state, &s);
+    if (apply_rowsum) {
+        rc = launch_update(s, M, K, (double)B_global, 0, flags, st);
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned)((B + 7) / 8), (unsigned)M);
+    sinkhorn_expand_kernel<<<grid, 256, 0, st>>>(table, B, M, K, RC_LOG2E / eps, s.lu, Q);
+    RC_CHECK_LAUNCH("sinkhorn_expand_kernel");
+    return RC_OK;
 }
 
 RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,

@@ -78,18 +78,25 @@ __device__ __forceinline__ void exp2_fast_batch(double (&w)[N]) {
 // Latency-oriented single evaluation (Estrin's scheme: dependency depth 5 instead of 11) for the sparse
 // pass, where a lane evaluates ONE significant element per table row and the chain latency, not the
 // fp64 pipe, is what a row costs.  Same coefficients; w < 1024 guaranteed by the caller.
+// coefficients in the constant bank: DFMA takes a c[][] operand directly, so the sparse pass (which runs at
+// 3 CTAs/SM and cannot keep 12 fp64 constants in registers) does not rematerialise them every row
+__constant__ double RC_EXP2_C[12] = {
+    1.0, 0.6931471805599453, 0.24022650695910158, 0.055504108664821625, 0.009618129107587256,
+    0.001333355814640647, 0.00015403530463724353, 1.5252733841556773e-05, 1.3215432535912375e-06,
+    1.0178057087733941e-07, 7.074194297288521e-09, 4.4558179083360645e-10};
+
 __device__ __forceinline__ double exp2_fast_estrin(double w) {
     const double MAGIC = 6755399441055744.0;
     const double t = w + MAGIC;
     const int n = max(__double2loint(t), -1022);
     const double f = w - (t - MAGIC);
     const double f2 = f * f;
-    const double p01 = fma(0.6931471805599453, f, 1.0);
-    const double p23 = fma(0.055504108664821625, f, 0.24022650695910158);
-    const double p45 = fma(0.001333355814640647, f, 0.009618129107587256);
-    const double p67 = fma(1.5252733841556773e-05, f, 0.00015403530463724353);
-    const double p89 = fma(1.0178057087733941e-07, f, 1.3215432535912375e-06);
-    const double pab = fma(4.4558179083360645e-10, f, 7.074194297288521e-09);
+    const double p01 = fma(RC_EXP2_C[1], f, RC_EXP2_C[0]);
+    const double p23 = fma(RC_EXP2_C[3], f, RC_EXP2_C[2]);
+    const double p45 = fma(RC_EXP2_C[5], f, RC_EXP2_C[4]);
+    const double p67 = fma(RC_EXP2_C[7], f, RC_EXP2_C[6]);
+    const double p89 = fma(RC_EXP2_C[9], f, RC_EXP2_C[8]);
+    const double pab = fma(RC_EXP2_C[11], f, RC_EXP2_C[10]);
     const double f4 = f2 * f2;
     const double q0 = fma(p23, f2, p01);
     const double q1 = fma(p67, f2, p45);

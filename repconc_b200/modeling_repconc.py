@@ -148,23 +148,20 @@ def center_distance_for_constraint(distances):
 
 @torch.no_grad()
 def sinkhorn_algorithm(out: Tensor, epsilon: float, sinkhorn_iterations: int, use_distrib_train: bool):
-    """modeling_repconc.py:137-165 as a function: `out` (M, K, B) = -centred distances (fp64 or fp32
-    values in [-1, 1]); returns Q (M, K, B) fp64 with columns summing to 1.
+    """modeling_repconc.py:137-165 as a function: `out` (M, K, B) = -centred distances (values in
+    [-1, 1], fp64 or fp32); returns Q (M, K, B) fp64 with columns summing to 1.
 
     The training path (RepCONC.quantize) never materialises Q; this entry point exists for callers
-    that want the transport plan itself.  It runs the same kernels on a table rebuilt from `out`
-    and then expands Q = exp(out/eps + lu[k] + lv[b]) * B from the scaling vectors."""
+    that want the transport plan itself.  It runs the same kernels on the (M,B,K) fp32 table rebuilt
+    from `out` and expands Q from the row scaling with rc_sinkhorn_expand."""
     ops._require_cuda(out, "out")
     lib = ops._lib.load()
     M, K, B = out.shape
     world = dist.get_world_size() if use_distrib_train else 1
-    # the kernels consume the (M,B,K) fp32 centred table; `out` is its negated transpose
-    table = (-out).transpose(1, 2).float().contiguous()
+    _identity_centring_check()
     with torch.cuda.device(out.device):
-        nbytes = lib.rc_sinkhorn_state_bytes(B, M, K)
-        state = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
-        flags = torch.zeros(1, dtype=torch.int32, device=out.device)
-        # identity centring: max = 1 - 1e-5.., chosen so (d - 0) / 1 leaves the table untouched
+        state = torch.empty(lib.rc_sinkhorn_state_bytes(B, M, K), dtype=torch.uint8, device=out.device)
+        # identity centring: middle = 0 and amplitude = 1 in fp32, so rc_sinkhorn_begin leaves the table as is
         minmax = torch.empty((2, M), dtype=torch.float32, device=out.device)
         minmax[0] = 1.0 - 1e-5
         minmax[1] = -(1.0 - 1e-5)
@@ -172,30 +169,36 @@ def sinkhorn_algorithm(out: Tensor, epsilon: float, sinkhorn_iterations: int, us
         base = state.data_ptr()
         off = lib.rc_sinkhorn_rowsum_ptr(base, B, M, K) - base
         P = state[off: off + M * K * 8].view(torch.float64).view(M, K)
-        _identity_centring_check(minmax)
-        ops._lib.check(lib.rc_sinkhorn_begin(table.data_ptr(), minmax.data_ptr(), B, M, K, float(epsilon), base,
-                                             flags.data_ptr(), sp), "rc_sinkhorn_begin")
-        for it in range(max(sinkhorn_iterations - 1, 0)):
-            if use_distrib_train:
-                dist.all_reduce(P)
-            ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), it, base,
-                                                flags.data_ptr(), sp), "rc_sinkhorn_step")
-        if use_distrib_train and sinkhorn_iterations >= 1:
-            dist.all_reduce(P)
-        # scaling vectors (log2 units) live in the state: lu (M,K) first, then P, then lv (M,B)
-        lu = state[: M * K * 8].view(torch.float64).view(M, K).clone()
-        lv_off = off + ((M * K * 8 + 255) // 256) * 256
-        lv = state[lv_off: lv_off + M * B * 8].view(torch.float64).view(M, B)
-        if sinkhorn_iterations >= 1:
-            lu = lu - torch.log2(K * P)
-        # final expansion (plumbing; not on the training path): one more column normalisation
-        log2e = 1.4426950408889634
-        Q = torch.exp2(out.double() * (log2e / epsilon) + lu[:, :, None] + lv[:, None, :])
-        Q = Q / Q.sum(dim=1, keepdim=True)
+        Q = torch.empty((M, K, B), dtype=torch.float64, device=out.device)
+        dense_prev = None
+        try:
+            while True:
+                # the kernels consume the (M,B,K) fp32 centred table; `out` is its negated transpose
+                table = (-out).transpose(1, 2).float().contiguous()
+                flags = torch.zeros(1, dtype=torch.int32, device=out.device)
+                ops._lib.check(lib.rc_sinkhorn_begin(table.data_ptr(), minmax.data_ptr(), B, M, K, float(epsilon),
+                                                     base, flags.data_ptr(), sp), "rc_sinkhorn_begin")
+                for it in range(max(sinkhorn_iterations - 1, 0)):
+                    if use_distrib_train:
+                        dist.all_reduce(P)
+                    ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), it,
+                                                        base, flags.data_ptr(), sp), "rc_sinkhorn_step")
+                if use_distrib_train and sinkhorn_iterations >= 1:
+                    dist.all_reduce(P)
+                ops._lib.check(lib.rc_sinkhorn_expand(table.data_ptr(), B, B * world, M, K, float(epsilon),
+                                                      1 if sinkhorn_iterations >= 1 else 0, base, Q.data_ptr(),
+                                                      flags.data_ptr(), sp), "rc_sinkhorn_expand")
+                if int(flags.item()) & ops.FLAG_SPARSE_UNSAFE and dense_prev is None:
+                    dense_prev = lib.rc_sinkhorn_set_dense(1)     # redo with the dense pass
+                    continue
+                break
+        finally:
+            if dense_prev is not None:
+                lib.rc_sinkhorn_set_dense(dense_prev)
     return Q
 
 
-def _identity_centring_check(minmax):
+def _identity_centring_check():
     # middle = (max + min) / 2 == 0 and amplitude = max - middle + 1e-5 == 1 in fp32
     mx = np.float32(1.0) - np.float32(1e-5)
     assert np.float32(mx + np.float32(1e-5)) == np.float32(1.0)

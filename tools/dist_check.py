@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun on N >= 2 GPUs of one box):
+  * constrained assign, batch sharded over ranks, NCCL all-reduces -> codes identical to the codes the
+    REFERENCE produced on 2 gloo ranks (golden assign_dist2_ds16) and to the oracle on the global batch;
+  * corpus-sharded ADC search + all_gather + merge -> identical to the oracle's unsharded search.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import golden_cases as GC  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle import oracle as O
+    from repconc_b200 import ops
+    from repconc_b200 import evaluate_repconc as E
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    ok = True
+    # --- assign
+    case = GC.DIST_CASES["dist2_ds16"]
+    x, c = GC.assign_inputs(case)
+    per = case["B"] // world
+    xs = torch.from_numpy(x[rank * per:(rank + 1) * per]).to(dev)
+    codes = ops.constrained_assign(xs, torch.from_numpy(c).to(dev), case["eps"], case["iters"])   # dist on
+    allc = [torch.empty_like(codes.contiguous()) for _ in range(world)]
+    dist.all_gather(allc, codes.contiguous())
+    got = torch.cat(allc, 0).cpu().numpy()
+    want = O.constrained_assign(x[: per * world], c, case["eps"], case["iters"])["codes"]
+    a_ok = bool(np.array_equal(got, want))
+    if world == 2:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "assign_dist2_ds16.npz"))
+        a_ok = a_ok and bool(np.array_equal(got, g["codes_conc"].astype(np.int64)))
+    ok &= a_ok
+    # --- larger assign (BASELINE config 5 shape per rank, fewer iterations), vs single-process global batch
+    gen = torch.Generator(device=dev).manual_seed(3)
+    cg = torch.randn((96, 256, 8), generator=gen, device=dev)
+    xg = torch.randn((world * 1024, 768), generator=gen, device=dev)                 # same on every rank
+    cd = ops.constrained_assign(xg[rank * 1024:(rank + 1) * 1024], cg, 0.003, 12)
+    cs = ops.constrained_assign(xg, cg, 0.003, 12, distributed=False)[rank * 1024:(rank + 1) * 1024]
+    b_ok = bool(torch.equal(cd, cs))
+    ok &= b_ok
+    # --- sharded ADC
+    q, cc, codes_h = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    lo, hi = E.shard_bounds(len(codes_h), rank, world)
+    shard = GpuIndexPQ(torch.from_numpy(codes_h[lo:hi]).to(dev), torch.from_numpy(cc).to(dev), id_offset=lo)
+    s, i = E.sharded_search(shard, q, 100)
+    so, io = O.adc_search(q, cc, codes_h, 100)
+    s_ok = bool(np.array_equal(s.cpu().numpy(), so) and np.array_equal(i.cpu().numpy(), io))
+    ok &= s_ok
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"dist_check world={world}: assign_golden={a_ok} assign_global_batch={b_ok} sharded_adc={s_ok} "
+              f"-> {'PASS' if flag.item() == 1 else 'FAIL'}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
