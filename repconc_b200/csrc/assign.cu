@@ -291,8 +291,19 @@ struct SkState {
     double* P;        // (M,K)   row sums (all-reduce operand)
     double* lv;       // (M,B)   log2 column scaling
     double* partial;  // (G,S,K) per-CTA row-sum partials
-    double* cut;      // (M)     log2 significance threshold of the sparse pass
+    double* drift;    // (M,2)   {max_k, max_k - min_k} of lu - lu_build      (sparse pass)
+    double* lu_build; // (M,K)   lu at the last survivor selection             (sparse pass)
+    unsigned long long* cursor;  // pool allocation cursor
+    uint32_t* csr_ptr;   // (M,B) first pool entry of a row
+    uint32_t* csr_cnt;   // (M,B) number of survivors of a row
+    uint8_t* pool_k;     // (pool) survivor column
+    double* pool_e;      // (pool) its value 2^(w - rowmax) at selection time
+    double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
+    uint64_t pool_cap;
 };
+
+constexpr unsigned int SK_POOL_CHUNK = 1024;  // pool entries a warp grabs per atomic (>= 256 = one full row)
+constexpr int SK_POOL_PER_ROW = 64;  // survivor pool sized for this many entries per table row on average
 
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
     size_t off = 0;
@@ -312,9 +323,29 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
     }
     (void)p;
     const size_t o_pa = take(pa);
-    const size_t o_cut = take((size_t)M * 8);
+    const size_t o_drift = take((size_t)M * 16 + 16);   // + {int decision, int block counter}
+    const size_t o_lub = take((size_t)M * K * 8);
+    const size_t o_cur = take(256);
+    // every warp of the selection pass may strand up to one chunk
+    uint64_t pool = (uint64_t)M * (uint64_t)B * SK_POOL_PER_ROW +
+                    (uint64_t)num_sms() * SK_MAX_CTAS_PER_SM * SK_WARPS * SK_POOL_CHUNK;
+    if (pool > 0xFFFFFF00ull) pool = 0xFFFFFF00ull;      // csr_ptr is 32-bit
+    const bool csr = (K == 256);
+    const size_t o_ptr = take(csr ? (size_t)M * B * 4 : 0);
+    const size_t o_cnt = take(csr ? (size_t)M * B * 4 : 0);
+    const size_t o_U = take((size_t)M * K * 8);
+    const size_t o_pk = take(csr ? (size_t)pool : 0);
+    const size_t o_pd = take(csr ? (size_t)pool * 8 : 0);
     if (s) {
-        s->cut = (double*)(b + o_cut);
+        s->drift = (double*)(b + o_drift);
+        s->lu_build = (double*)(b + o_lub);
+        s->cursor = (unsigned long long*)(b + o_cur);
+        s->csr_ptr = (uint32_t*)(b + o_ptr);
+        s->csr_cnt = (uint32_t*)(b + o_cnt);
+        s->U = (double*)(b + o_U);
+        s->pool_k = (uint8_t*)(b + o_pk);
+        s->pool_e = (double*)(b + o_pd);
+        s->pool_cap = pool;
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
         s->lv = (double*)(b + o_lv);
@@ -562,10 +593,29 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 //   4. normalises by the column sum and adds Q / (B * sum) to the warp's private row-sum array.
 // The column scaling lv is not needed at all here: each column is normalised by its own sum, and the
 // row maximum keeps 2^w in range.  Accumulation order per (warp, k) is the row order -> deterministic.
+//
+// Survivor lists are REUSED across iterations.  The selection pass keeps everything within
+// SK_MARGIN + SK_SLACK of the row maximum and emits the (k, d~) pairs of each row into a pool (CSR: per-row
+// offset / count / fp32 maximum).  Between selections only lu changes: an element left out had
+// w - rowmax < -(MARGIN + SLACK) at selection time, and afterwards w - rowmax can grow by at most
+// spread = max_k(dlu) - min_k(dlu), dlu = lu - lu_build.  sinkhorn_update_kernel tracks that spread per
+// sub-vector; while max_m spread <= SK_SLACK the cheap pass (sinkhorn_step_csr_kernel) iterates on the
+// lists alone -- no table read, no filter -- otherwise the selection pass runs again.  Both kernels are
+// launched every iteration and decide on the device (same inputs, same decision) which one works.
 // The dense kernel above remains the path for K != 256, for RC_SINKHORN_DENSE=1 and for the re-run
 // after RC_FLAG_SPARSE_UNSAFE.
 // ---------------------------------------------------------------------------------------------
 constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
+constexpr double SK_SLACK = 24.0;        // extra selection depth = admissible drift of lu between selections
+
+// true -> this iteration re-selects (and re-emits) the survivors; false -> it iterates on the lists
+// (the decision is made once per iteration by the last block of sinkhorn_update_kernel and published as
+//  one int behind the drift array: drift[2*M] reinterpreted)
+__device__ __forceinline__ bool csr_reselect(const double* __restrict__ drift, int M, int force) {
+    if (force) return true;
+    return reinterpret_cast<const int*>(drift + 2 * M)[0] != 0;
+}
+
 constexpr double SK_UNSAFE_LOG2 = -8.0;  // a row that keeps < 2^-8 / K of mass voids the row-sum bound
 constexpr int SP_CTAS_PER_SM = 3;
 constexpr int SP_K = 256;
@@ -578,9 +628,10 @@ constexpr int SP_SMEM = SP_OFF_BAR + SK_WARPS * SK_DEPTH * 8;
 
 __global__ void __launch_bounds__(SK_THREADS, SP_CTAS_PER_SM)
 sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2,
-                            SkPart part, const double* __restrict__ lu_g, double* __restrict__ partial,
-                            int32_t* __restrict__ flags) {
+                            SkPart part, const double* __restrict__ lu_g, const double* __restrict__ drift,
+                            int force, SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char sp_smem[];
+    if (!csr_reselect(drift, M, force)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* my_ring = reinterpret_cast<float*>(sp_smem) + warp * SK_DEPTH * SP_K;
     double* acc_all = reinterpret_cast<double*>(sp_smem + SP_OFF_ACC);
@@ -602,7 +653,9 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
     const float scale32 = (float)scale2;
     const uint32_t row_bytes = SP_K * 4u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const float sel_margin = (float)SK_MARGIN + 0.5f;
+    const float sel_margin = (float)(SK_MARGIN + SK_SLACK) + 0.5f;
+    unsigned long long chunk_base = 0;   // this warp's current pool chunk
+    unsigned int chunk_left = 0;
 
     int64_t t = t_lo;
     while (t < t_hi) {
@@ -677,6 +730,35 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
                 s += q;
                 my_q[idx] = q;
             }
+            // 3b. emit the survivor list of this row: (k, 2^(w - rowmax)) pairs.  Pool space comes in per-warp
+            //     chunks (one atomic per ~50 rows); the order of rows in the pool is irrelevant, the order inside
+            //     a row is the ballot order -> deterministic sums
+            {
+                if ((unsigned int)total > chunk_left) {
+                    unsigned long long nb = 0;
+                    if (lane == 0) nb = atomicAdd(st.cursor, (unsigned long long)SK_POOL_CHUNK);
+                    chunk_base = __shfl_sync(0xffffffffu, nb, 0);
+                    chunk_left = SK_POOL_CHUNK;
+                }
+                const unsigned long long off = chunk_base;
+                const int64_t row_id = (int64_t)m * B + b_first + (int64_t)r * SK_WARPS;
+                const bool fits = off + (unsigned long long)total <= st.pool_cap;
+                if (fits) {
+                    if (lane < total) { st.pool_k[off + lane] = (uint8_t)k0; st.pool_e[off + lane] = q0; }
+                    for (int idx = 32 + lane; idx < total; idx += 32) {
+                        st.pool_k[off + idx] = my_kl[idx];
+                        st.pool_e[off + idx] = my_q[idx];
+                    }
+                } else {
+                    bad |= RC_FLAG_SPARSE_UNSAFE;   // pool exhausted: the host re-runs densely
+                }
+                if (lane == 0) {
+                    st.csr_ptr[row_id] = (uint32_t)off;
+                    st.csr_cnt[row_id] = fits ? (uint32_t)total : 0u;
+                }
+                chunk_base += (unsigned long long)total;
+                chunk_left -= (unsigned int)total;
+            }
             s = warp_sum(s);
             if (!(s >= 0.5) || !isfinite(s)) bad |= RC_FLAG_NONFINITE;   // the maximum itself contributes ~1
             // 4. Q / (B_global * column sum) into the row sums (:155, :162-163)
@@ -711,10 +793,121 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
     if (bad) atomicOr(flags, bad);
 }
 
+// Iteration on the survivor lists alone (see the comment above sinkhorn_step_sparse_kernel).
+// A list entry carries E = 2^(w - rowmax) as evaluated (fp64) by the selection pass; since then only lu
+// moved, so the element's current value is E * 2^(lu[k] - lu_build[k]) -- up to a per-row constant that
+// the column normalisation removes.  U[k] = 2^(dlu[k] - max_k dlu) is evaluated once per iteration by
+// sinkhorn_update_kernel (256 values per sub-vector), which leaves ONE multiplication per entry here.
+// Granularity: a row has ~40 survivors, so a QUARTER-warp (8 lanes) owns a row and a warp works on four
+// rows at once -- the per-row bookkeeping (offsets, the 3-step shuffle reduction, the reciprocal) is then
+// shared by four rows per instruction.  Each quarter-warp has its own private row-sum array (4 rows of a
+// warp may hit the same column), 32 arrays per CTA, summed in fixed order at the end.
+constexpr int CSR_CTAS_PER_SM = 3;
+constexpr int CSR_PER_LANE = 16;   // entries a lane holds in registers (8 lanes x 16 = 128 per row)
+constexpr int CSR_SMEM = SK_WARPS * 4 * SP_K * 8 + SP_K * 8;   // 64 KB of row sums + U
+
+__global__ void __launch_bounds__(SK_THREADS, CSR_CTAS_PER_SM)
+sinkhorn_step_csr_kernel(int64_t B, double rBg, int M, SkPart part, const double* __restrict__ drift, int force,
+                         SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char csr_smem[];
+    double* acc_all = reinterpret_cast<double*>(csr_smem);                 // [32 quarter-warps][256]
+    double* U_s = acc_all + SK_WARPS * 4 * SP_K;
+    if (csr_reselect(drift, M, force)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane >> 3, l8 = lane & 7;                               // quarter-warp, lane inside it
+    double* my_acc = acc_all + (warp * 4 + sub) * SP_K;
+    const int g = blockIdx.x;
+    const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
+    if (t_lo >= t_hi) return;
+    const int m_first = (int)(t_lo / part.tpm);
+    int bad = 0;
+
+    int64_t t = t_lo;
+    while (t < t_hi) {
+        const int m = (int)(t / part.tpm);
+        const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
+        // rows [b_lo, b_hi) of sub-vector m belong to this CTA; quarter-warp q = warp*4+sub takes b_lo+q, +32, ...
+        const int64_t b_lo = (t - (int64_t)m * part.tpm) * SK_WARPS;
+        const int64_t b_hi = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        U_s[threadIdx.x] = st.U[(int64_t)m * SP_K + threadIdx.x];
+        for (int i = l8; i < SP_K; i += 8) my_acc[i] = 0.0;
+        __syncthreads();
+        const int64_t rbase = (int64_t)m * B;
+        // Row meta is fetched one iteration ahead; a lane's first CSR_PER_LANE entries (128 per row) are all
+        // loaded up front into registers -- ONE memory latency per iteration -- and reused for the row-sum
+        // update.  Rows with more survivors than that finish in a (rare) tail loop.
+        uint32_t ptr_n = 0;
+        int cnt_n = 0;
+        {
+            const int64_t b = b_lo + warp * 4 + sub;
+            if (b < b_hi) { ptr_n = st.csr_ptr[rbase + b]; cnt_n = (int)st.csr_cnt[rbase + b]; }
+        }
+        for (int64_t b0 = b_lo + warp * 4; b0 < b_hi; b0 += 32) {   // warp-uniform trip count
+            const bool live = b0 + sub < b_hi;
+            const uint32_t ptr = ptr_n;
+            const int total = cnt_n;
+            {
+                const int64_t bn = b0 + 32 + sub;
+                const bool ln = bn < b_hi;
+                ptr_n = ln ? st.csr_ptr[rbase + bn] : 0u;
+                cnt_n = ln ? (int)st.csr_cnt[rbase + bn] : 0;
+            }
+            const uint8_t* pk = st.pool_k + ptr;
+            const double* pe = st.pool_e + ptr;
+            int kk[CSR_PER_LANE];
+            double qq[CSR_PER_LANE];
+#pragma unroll
+            for (int i = 0; i < CSR_PER_LANE; ++i) {
+                const int idx = l8 + 8 * i;
+                const bool v = idx < total;
+                kk[i] = v ? (int)pk[idx] : 0;
+                qq[i] = v ? pe[idx] : 0.0;
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < CSR_PER_LANE; ++i) {
+                qq[i] *= U_s[kk[i]];
+                s += qq[i];
+            }
+            for (int idx = 8 * CSR_PER_LANE + l8; idx < total; idx += 8) s = fma(pe[idx], U_s[pk[idx]], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (live && (!(s > 0.0) || !isfinite(s))) bad |= RC_FLAG_NONFINITE;
+            const double rz = __drcp_rn(s) * rBg;
+#pragma unroll
+            for (int i = 0; i < CSR_PER_LANE; ++i)
+                if (l8 + 8 * i < total) my_acc[kk[i]] = fma(qq[i], rz, my_acc[kk[i]]);
+            for (int idx = 8 * CSR_PER_LANE + l8; idx < total; idx += 8) {
+                const int k = pk[idx];
+                my_acc[k] = fma(pe[idx] * U_s[k], rz, my_acc[k]);
+            }
+        }
+        __syncthreads();
+        {
+            double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * SP_K;
+            double sum = acc_all[threadIdx.x];
+#pragma unroll 8
+            for (int w = 1; w < SK_WARPS * 4; ++w) sum += acc_all[w * SP_K + threadIdx.x];
+            dst[threadIdx.x] = sum;
+        }
+        __syncthreads();
+        t = t_end;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
 // P[m,k] = sum over the CTAs that touched sub-vector m, in CTA order (deterministic).
 __global__ void __launch_bounds__(256)
-sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, double* __restrict__ P) {
+sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, double* __restrict__ P,
+                       int csr_mode, int M, int force, SkState st) {
     const int m = blockIdx.x;
+    if (csr_mode) {
+        // the pass that just ran re-selected the survivors iff csr_reselect() says so: remember its lu
+        if (csr_reselect(st.drift, M, force))
+            for (int k = threadIdx.x; k < K; k += blockDim.x) st.lu_build[(int64_t)m * K + k] = st.lu[(int64_t)m * K + k];
+        if (m == 0 && threadIdx.x == 0) *st.cursor = 0ull;   // only live during a selection pass
+    }
     const int64_t m_lo = (int64_t)m * part.tpm, m_hi = m_lo + part.tpm;
     // only CTAs whose tile range [total*g/G, total*(g+1)/G) can touch [m_lo, m_hi)
     int g_first = (int)((m_lo * part.G) / part.total) - 1;
@@ -734,18 +927,18 @@ sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, d
 }
 
 // row normalisation in log2 form: lu[m,k] -= log2(K * P[m,k])     (Q /= sum_of_rows; Q /= K, :158-159)
-// Also derives, per sub-vector, the significance threshold of the sparse pass that follows:
-// the previous column normalisation left every column of Q summing to exactly 1/B_global, this update
-// multiplies row k by 2^dlu[k], so every new column sum is >= 2^(min_k dlu) / B_global; an element with
-// log2 Q < cut = -log2(B_global) + min_k dlu - SK_MARGIN is below 2^-SK_MARGIN of its column sum.
-
-
+// Also tracks, per sub-vector, how far lu has moved since the last survivor selection
+// (drift[m] = {max_k, max_k - min_k} of lu - lu_build), which is what decides between the list pass and a
+// new selection, and checks that every centroid kept a sane share of the mass through the last column
+// normalisation (the premise of the sparse pass's row-sum bound).
 __global__ void __launch_bounds__(256)
-sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, int K, double Kd, double log2Bg,
-                       int check_mass, double* __restrict__ cut, int32_t* __restrict__ flags) {
-    __shared__ double red[8];
+sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, const double* __restrict__ lu_build,
+                       int K, double Kd, int check_mass, double* __restrict__ drift, double* __restrict__ U,
+                       int32_t* __restrict__ flags) {
+    __shared__ double red_mx[8], red_mn[8];
+    __shared__ double s_dmax;
     const int m = blockIdx.x;
-    double dmin = INFINITY;
+    double dmax = -INFINITY, dmin = INFINITY;
     int bad = 0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const int64_t i = (int64_t)m * K + k;
@@ -753,16 +946,47 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, in
         if (!(z > 0.0) || !isfinite(z)) bad |= RC_FLAG_NONFINITE;
         const double dl = -log2(z);
         if (check_mass && dl > -SK_UNSAFE_LOG2) bad |= RC_FLAG_SPARSE_UNSAFE;   // K*P[k] < 2^-8
-        lu[i] += dl;
-        dmin = fmin(dmin, dl);
+        const double nl = lu[i] + dl;
+        lu[i] = nl;
+        const double dv = nl - lu_build[i];
+        dmax = fmax(dmax, dv);
+        dmin = fmin(dmin, dv);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dmin;
+    for (int o = 16; o > 0; o >>= 1) {
+        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    }
+    if ((threadIdx.x & 31) == 0) { red_mx[threadIdx.x >> 5] = dmax; red_mn[threadIdx.x >> 5] = dmin; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) dmin = fmin(dmin, red[w]);
-        cut[m] = -log2Bg + dmin - SK_MARGIN;
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            dmax = fmax(dmax, red_mx[w]);
+            dmin = fmin(dmin, red_mn[w]);
+        }
+        drift[2 * m] = dmax;
+        drift[2 * m + 1] = dmax - dmin;
+        s_dmax = dmax;
+        // last block to finish publishes the iteration's decision: re-select iff any spread exceeds the slack
+        int* ctl = reinterpret_cast<int*>(drift + 2 * gridDim.x);
+        __threadfence();
+        if (atomicAdd(ctl + 1, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            int resel = 0;
+            for (int i = 0; i < (int)gridDim.x; ++i) {
+                const double sp = reinterpret_cast<volatile double*>(drift)[2 * i + 1];
+                if (!(sp <= SK_SLACK)) resel = 1;   // also NaN
+            }
+            ctl[0] = resel;
+            ctl[1] = 0;
+        }
+    }
+    __syncthreads();
+    // per-column factor of the list pass: 2^(dlu - max dlu) in (0, 1]
+    const double dm = s_dmax;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int64_t i = (int64_t)m * K + k;
+        U[i] = exp2(lu[i] - lu_build[i] - dm);
     }
     if (bad) atomicOr(flags, bad);
 }
@@ -829,15 +1053,17 @@ static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, 
     return RC_OK;
 }
 
-static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaStream_t st) {
-    sinkhorn_reduce_kernel<<<M, 256, 0, st>>>(s.partial, p, K, s.P);
+static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaStream_t st, int csr_mode = 0,
+                         int force = 0) {
+    sinkhorn_reduce_kernel<<<M, 256, 0, st>>>(s.partial, p, K, s.P, csr_mode, M, force, s);
     RC_CHECK_LAUNCH("sinkhorn_reduce_kernel");
     return RC_OK;
 }
 
 static int launch_update(const SkState& s, int M, int K, double Bg, int check_mass, int32_t* flags,
                          cudaStream_t st) {
-    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, K, (double)K, log2(Bg), check_mass, s.cut, flags);
+    (void)Bg;
+    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, s.lu_build, K, (double)K, check_mass, s.drift, s.U, flags);
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
 }
@@ -957,6 +1183,10 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
     const int64_t n = (int64_t)M * K;
     fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, n, 0.0);
     RC_CHECK_LAUNCH("fill_f64_kernel");
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu_build, n, 0.0);
+    RC_CHECK_LAUNCH("fill_f64_kernel");
+    RC_CUDA(cudaMemsetAsync(s.drift + 2 * M, 0, 16, st));
+    RC_CUDA(cudaMemsetAsync(s.cursor, 0, 8, st));
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
     return launch_reduce(p, s, M, K, st);
@@ -982,13 +1212,22 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
         if (!attr_done) {
             RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SP_SMEM));
+            RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CSR_SMEM));
             attr_done = true;
         }
+        // selection pass and list pass are both launched; exactly one of them works (device-side decision
+        // from the drift the update kernel just wrote; the first step always selects)
         const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM);
-        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, 1.0 / (double)B_global, M,
-                                                                      RC_LOG2E / eps, ps, s.lu, s.partial, flags);
+        const int force = step_index == 0 ? 1 : 0;
+        const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
+        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, rBg, M, scale2, ps, s.lu, s.drift,
+                                                                      force, s, s.partial, flags);
         RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
-        return launch_reduce(ps, s, M, K, st);
+        sinkhorn_step_csr_kernel<<<ps.G, SK_THREADS, CSR_SMEM, st>>>(B, rBg, M, ps, s.drift, force, s, s.partial,
+                                                                    flags);
+        RC_CHECK_LAUNCH("sinkhorn_step_csr_kernel");
+        return launch_reduce(ps, s, M, K, st, 1, force);
     }
     rc = launch_pass<SK_STEP>(const_cast<float*>(table), nullptr, B, (double)B_global, M, K, eps, p, s, nullptr,
                               nullptr, flags, st);
