@@ -21,6 +21,7 @@
 //   select/gather/sort  exact top-k: 4-pass radix select over fp32 keys, tie-exact ordered gather,
 //                       bitonic sort of <= 8192 composite keys (score desc, id asc).
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -344,6 +345,116 @@ adc_scan_packed_kernel(PackScanArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bank-conflict-free variant of the packed scan (M % 8 == 0, 8 queries per entry).
+// The thread-per-document kernel above gathers at random 16-byte bank groups: ncu shows 2.5 wavefronts
+// per ideal wavefront and the LSU wavefront pipe at 98.8 % -- it IS the shared-memory crossbar limit.
+// Here the table is laid out [k][m] (m fastest) and the 8 lanes of a quarter-warp take 8 CONSECUTIVE
+// sub-vectors of ONE document: entry index = code*M + m, so the bank group (index mod 8) equals the lane
+// index inside the quarter whatever the codes are -- every LDS.128 phase is conflict-free.  A warp works
+// on 4 documents at a time; each lane accumulates M/8 entries, then the 8 partial 4-word accumulators
+// of a document are reduced with a halving exchange (4 shuffles instead of 12) that leaves lane j of the
+// quarter with the complete 16-bit sums of query j -- which it compares with that query's threshold.
+// ---------------------------------------------------------------------------------------------
+constexpr int CF_THREADS = 1024;   // 32 warps: the gathers are latency-bound at 16
+
+template <int MT>
+__global__ void __launch_bounds__(CF_THREADS, 1)
+adc_scan_cf_kernel(PackScanArgs a) {
+    static_assert(MT % 8 == 0, "8 consecutive sub-vectors per quarter-warp");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint4* lutS = reinterpret_cast<const uint4*>(smem_raw);  // [256][MT], 8 x uint16 per entry
+    const int64_t q0 = (int64_t)blockIdx.x * 8;
+    const int nqt = (int)min((int64_t)8, a.nq - q0);
+    {
+        uint16_t* lh = reinterpret_cast<uint16_t*>(smem_raw);
+        const int n = MT * ADC_K;
+        for (int qq = 0; qq < 8; ++qq) {
+            const uint16_t* src = a.qlut + (q0 + qq) * (int64_t)n;
+            for (int i = threadIdx.x; i < n; i += CF_THREADS) {
+                const int m = i >> 8, k = i & 255;
+                lh[(k * MT + m) * 8 + qq] = qq < nqt ? src[i] : (uint16_t)0;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & 7, sub = lane >> 3;
+    const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0;
+    const int my_thr = j < nqt ? a.thr_i[q0 + j] : 0x7fffffff;   // lane j of a quarter owns query j
+    __syncthreads();
+
+    const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
+    const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
+    constexpr int DOCS_PER_IT = (CF_THREADS / 32) * 4;   // 128 documents per CTA iteration, 4 per warp
+
+    // one group of 4 documents: gather, halving exchange over the quarter-warp (after it lane j holds the
+    // 16-bit sum of query j), threshold test
+    auto scan_group = [&](const uint32_t (&cb)[MT / 8], int64_t p, bool live) {
+        uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+        for (int i = 0; i < MT / 8; ++i) {
+            const uint4 v = lutS[cb[i] * MT + 8 * i + j];
+            acc0 += v.x; acc1 += v.y; acc2 += v.z; acc3 += v.w;
+        }
+        const uint32_t s0 = b2 ? acc0 : acc2, s1 = b2 ? acc1 : acc3;
+        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+        const uint32_t k0 = (b2 ? acc2 : acc0) + r0, k1 = (b2 ? acc3 : acc1) + r1;
+        const uint32_t s2 = b1 ? k0 : k1;
+        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 2);
+        uint32_t w = (b1 ? k1 : k0) + r2;
+        w += __shfl_xor_sync(0xffffffffu, w, 1);
+        const int sum = (int)((w >> (16 * (j & 1))) & 0xffffu);
+        if (live && sum >= my_thr) {
+            const unsigned int pos = atomicAdd(a.cnt + q0 + j, 1u);
+            if (pos < (unsigned int)a.cap) a.cand[(q0 + j) * (int64_t)a.cap + pos] = (uint32_t)p;
+        }
+    };
+
+    // full iterations (every document of every warp's group is inside the split): no predicates, code bytes
+    // of the next group are loaded while this one is scanned
+    const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
+    int64_t p = p_lo + warp * 4 + sub;
+    const uint8_t* cp = a.codes + p * MT + j;
+    uint32_t cb[MT / 8], cn[MT / 8];
+    if (full > 0) {
+#pragma unroll
+        for (int i = 0; i < MT / 8; ++i) cb[i] = __ldg(cp + 8 * i);
+    }
+    for (int64_t t = 0; t < full; ++t) {
+        if (t + 1 < full) {
+#pragma unroll
+            for (int i = 0; i < MT / 8; ++i) cn[i] = __ldg(cp + (int64_t)DOCS_PER_IT * MT + 8 * i);
+        }
+        scan_group(cb, p, true);
+#pragma unroll
+        for (int i = 0; i < MT / 8; ++i) cb[i] = cn[i];
+        p += DOCS_PER_IT;
+        cp += (int64_t)DOCS_PER_IT * MT;
+    }
+    // tail: fewer than 64 documents left in the split
+    if (p_lo + full * DOCS_PER_IT < p_hi) {   // block-uniform
+        const bool live = p < p_hi;
+#pragma unroll
+        for (int i = 0; i < MT / 8; ++i) cb[i] = live ? (uint32_t)__ldg(cp + 8 * i) : 0u;
+        scan_group(cb, p, live);
+    }
+}
+
+template <int MT>
+static int launch_cf_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
+    auto kern = adc_scan_cf_kernel<MT>;
+    const size_t smem = (size_t)MT * ADC_K * 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((a.nq + 7) / 8), (unsigned)splits);
+    kern<<<grid, CF_THREADS, smem, st>>>(a);
+    RC_CHECK_LAUNCH("adc_scan_cf_kernel");
+    return RC_OK;
+}
+
 static int scan_qp(int M) {
     const size_t per_q = (size_t)M * ADC_K * 2;
     const size_t budget = 200 * 1024;
@@ -386,6 +497,16 @@ static void scan_splits(int64_t nq, int qt, int64_t npos, int M, int64_t* pps_ou
     *splits_out = splits;
 }
 
+// RC_ADC_GATHER=1 selects the thread-per-document packed scan (for A/B measurements)
+static bool adc_force_gather() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RC_ADC_GATHER");
+        v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static int launch_packed(PackScanArgs a, cudaStream_t st) {
     if (a.nq <= 0 || a.npos <= 0) return RC_OK;
     const int qp = scan_qp(a.M);
@@ -397,6 +518,17 @@ static int launch_packed(PackScanArgs a, cudaStream_t st) {
     scan_splits(a.nq, qp, a.npos, a.M, &pps, &splits);
     a.pos_per_split = pps;
 #define RC_PSCAN(QP, MT) return launch_packed_inst<QP, MT>(a, (int)splits, st)
+    if (qp == 8 && !adc_force_gather()) {
+        switch (a.M) {   // conflict-free layout
+            case 8: return launch_cf_inst<8>(a, (int)splits, st);
+            case 16: return launch_cf_inst<16>(a, (int)splits, st);
+            case 24: return launch_cf_inst<24>(a, (int)splits, st);
+            case 32: return launch_cf_inst<32>(a, (int)splits, st);
+            case 40: return launch_cf_inst<40>(a, (int)splits, st);
+            case 48: return launch_cf_inst<48>(a, (int)splits, st);
+            default: break;
+        }
+    }
     if (qp == 8) {
         switch (a.M) {
             case 8: RC_PSCAN(8, 8);
