@@ -251,16 +251,16 @@ def main():
     scan_avg_s = scan_ms / 1e3 / max(scan_launches, 1)
     achieved = alg_per_launch / scan_avg_s / 1e9 if scan_avg_s > 0 else 0.0
     # dram__bytes_read + dram__bytes_write of ONE launch (1200 queries x 8,841,823 docs) from the committed
-    # `ncu --set full` capture profiles/r01_adc_scan_packed_ncu.txt; scaled to this run's shard size
-    ncu_traffic = (523.925504e6 + 24.176896e6) * (n_shard / N_DOCS) if scan_launches == Ksteps else None
-    roofline = {"bound": "hbm", "kernel": "adc_scan_packed_kernel<8,48>", "achieved": achieved, "peak": hbm_peak,
+    # `ncu --set full` capture profiles/r01_adc_scan_cf_ncu.txt; scaled to this run's shard size
+    ncu_traffic = (520.220672e6 + 19.589632e6) * (n_shard / N_DOCS) if scan_launches == Ksteps else None
+    roofline = {"bound": "hbm", "kernel": "adc_scan_cf_kernel<48>", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": scan_avg_s * 1e3,
                 "share_of_step": scan_ms / adc_ms,
                 "note": "algorithmic bytes = every query streams every code byte once (SURVEY 8d); queries are "
-                        "tiled 8 per CTA and a split's codes stay L2-resident, so DRAM traffic is ~500x below "
-                        "this; the kernel is bound by the shared-memory crossbar (ncu: LSU wavefronts 98.8% of "
-                        "peak, 2.5-way bank conflicts from random codes), not by HBM"}
+                        "tiled 8 per CTA and a split's codes stay L2-resident, so DRAM traffic is ~900x below "
+                        "this; the kernel is bound by shared-memory bandwidth (ncu: LSU wavefronts 98% of peak "
+                        "with a bank-conflict-free table layout), not by HBM"}
 
     # ------------------------------------------------------------------ constrained assign (secondary)
     assign = None

@@ -836,18 +836,21 @@ sinkhorn_step_csr_kernel(int64_t B, double rBg, int M, SkPart part, const double
         // Row meta is fetched one iteration ahead; a lane's first CSR_PER_LANE entries (128 per row) are all
         // loaded up front into registers -- ONE memory latency per iteration -- and reused for the row-sum
         // update.  Rows with more survivors than that finish in a (rare) tail loop.
+        // Row order: warp w takes the rows the SAME warp of the selection pass took (b_lo + w, + 8, + 16, ...),
+        // four consecutive ones per iteration (one per quarter-warp).  The selection pass wrote exactly that
+        // sequence back to back into its pool chunk, so every warp here streams a contiguous region of HBM.
         uint32_t ptr_n = 0;
         int cnt_n = 0;
         {
-            const int64_t b = b_lo + warp * 4 + sub;
+            const int64_t b = b_lo + warp + (int64_t)SK_WARPS * sub;
             if (b < b_hi) { ptr_n = st.csr_ptr[rbase + b]; cnt_n = (int)st.csr_cnt[rbase + b]; }
         }
-        for (int64_t b0 = b_lo + warp * 4; b0 < b_hi; b0 += 32) {   // warp-uniform trip count
-            const bool live = b0 + sub < b_hi;
+        for (int64_t b0 = b_lo + warp; b0 < b_hi; b0 += 4 * SK_WARPS) {   // warp-uniform trip count
+            const bool live = b0 + (int64_t)SK_WARPS * sub < b_hi;
             const uint32_t ptr = ptr_n;
             const int total = cnt_n;
             {
-                const int64_t bn = b0 + 32 + sub;
+                const int64_t bn = b0 + (int64_t)SK_WARPS * (4 + sub);
                 const bool ln = bn < b_hi;
                 ptr_n = ln ? st.csr_ptr[rbase + bn] : 0u;
                 cnt_n = ln ? (int)st.csr_cnt[rbase + bn] : 0;

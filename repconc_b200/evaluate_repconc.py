@@ -67,7 +67,7 @@ def load_index_to_gpu(index, single_gpu_id: Optional[int] = None):
 def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarray, index, topk: int):
     """evaluate_repconc.py:180-185."""
     topk_scores, topk_idx = index.search(query_embeds, topk)
-    topk_ids = np.vstack([corpus_ids[x] for x in topk_idx])
+    topk_ids = corpus_ids[topk_idx]          # == np.vstack([corpus_ids[x] for x in topk_idx]) (:183)
     assert len(query_ids) == len(topk_scores) == len(topk_ids)
     return topk_scores, topk_ids
 

@@ -165,6 +165,7 @@ class GpuIndexPQ:
         self.metric_type = METRIC_INNER_PRODUCT
         self.is_trained = True
         self._ws = None
+        self._stage = {}
         self.last_stats = None
 
     @classmethod
@@ -217,16 +218,37 @@ class GpuIndexPQ:
             self.last_stats = dict(filtered=st[0], dense=st[1], max_candidates=st[2], sample=st[3])
         return scores, ids
 
+    def _pinned(self, name, shape, dtype):
+        """persistent page-locked staging buffers (allocated once, grown on demand): host arrays go through
+        them so that both directions are single asynchronous DMA copies"""
+        n = int(np.prod(shape))
+        buf = self._stage.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+            self._stage[name] = buf
+        return buf[:n].view(shape)
+
     def search(self, x, k):
         if isinstance(x, torch.Tensor):
             if not x.is_cuda:
                 x = x.to(self.device)
             return self.search_tensor(x, k)
         x = np.ascontiguousarray(x, dtype=np.float32)
-        xt = torch.from_numpy(x).pin_memory().to(self.device, non_blocking=True) if x.size else \
-            torch.empty(x.shape, device=self.device)
-        s, i = self.search_tensor(xt, k)
-        return s.cpu().numpy(), i.cpu().numpy()
+        if x.ndim != 2:
+            raise ValueError(f"query_embeds: expected (nq, d), got {x.shape}")
+        nq, k = x.shape[0], int(k)
+        if nq == 0:
+            return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+        with torch.cuda.device(self.device):
+            hx = self._pinned("x", x.shape, torch.float32)
+            hx.copy_(torch.from_numpy(x))
+            s, i = self.search_tensor(hx.to(self.device, non_blocking=True), k)
+            hs = self._pinned("s", (nq, k), torch.float32)
+            hi = self._pinned("i", (nq, k), torch.int64)
+            hs.copy_(s, non_blocking=True)
+            hi.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return hs.numpy().copy(), hi.numpy().copy()
 
 
 # ----------------------------------------------------------------------------------------------
