@@ -175,6 +175,10 @@ int rc_adc_lut(const float* queries, int64_t ldq, const float* centroids, int64_
 /* dense scores of docs [n0, n0+n) for all queries: out (nq, n) fp32 */
 int rc_adc_scores(const float* lut, const uint8_t* codes, int64_t nq, int64_t n0, int64_t n, int M,
                   float* out, void* stream);
+/* out[i] = corpus_ids[idx[i]]: the position -> external id mapping of evaluate_repconc.py:183 on the device
+ * (negative positions wrap like numpy indexing, as the reference's `corpus_ids[x]` does) */
+int rc_map_ids(const int64_t* idx, const int64_t* corpus_ids, int64_t n_corpus, int64_t n, int64_t* out,
+               void* stream);
 /* merge W per-shard sorted top-k lists (W, nq, k) into (nq, k); workspace-free */
 int rc_topk_merge(const float* scores_in, const int64_t* ids_in, int W, int64_t nq, int64_t k,
                   float* scores, int64_t* ids, void* stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
                               c_ptr, c_ptr, c_size, c_ptr]),
     "rc_adc_lut": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr]),
     "rc_adc_scores": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_ptr]),
+    "rc_map_ids": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "rc_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "rc_adc_last_stats": (None, [ctypes.POINTER(c_i64)]),
     "rc_adc_enable_timing": (None, [c_int]),

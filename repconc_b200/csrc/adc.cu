@@ -1188,6 +1188,26 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
     return RC_OK;
 }
 
+// external ids: out[i] = corpus_ids[idx[i]] (negative idx wraps like numpy's corpus_ids[-1], which is what
+// the reference's `corpus_ids[x]` does with Faiss' -1 padding, evaluate_repconc.py:183)
+__global__ void map_ids_kernel(const int64_t* __restrict__ idx, const int64_t* __restrict__ table, int64_t n_table,
+                               int64_t n, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t j = idx[i];
+    if (j < 0) j += n_table;
+    out[i] = (j >= 0 && j < n_table) ? table[j] : -1;
+}
+
+RC_API int rc_map_ids(const int64_t* idx, const int64_t* corpus_ids, int64_t n_corpus, int64_t n, int64_t* out,
+                      void* stream) {
+    RC_REQUIRE(idx && corpus_ids && out && n >= 0 && n_corpus >= 1, "rc_map_ids: bad argument");
+    if (n == 0) return RC_OK;
+    map_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(idx, corpus_ids, n_corpus, n, out);
+    RC_CHECK_LAUNCH("map_ids_kernel");
+    return RC_OK;
+}
+
 RC_API int rc_topk_merge(const float* scores_in, const int64_t* ids_in, int W, int64_t nq, int64_t k, float* scores,
                          int64_t* ids, void* stream) {
     RC_REQUIRE(scores_in && ids_in && scores && ids, "rc_topk_merge: null pointer");

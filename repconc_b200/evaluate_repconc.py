@@ -66,8 +66,13 @@ def load_index_to_gpu(index, single_gpu_id: Optional[int] = None):
 
 def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarray, index, topk: int):
     """evaluate_repconc.py:180-185."""
-    topk_scores, topk_idx = index.search(query_embeds, topk)
-    topk_ids = corpus_ids[topk_idx]          # == np.vstack([corpus_ids[x] for x in topk_idx]) (:183)
+    if (isinstance(index, faiss.GpuIndexPQ) and isinstance(query_embeds, np.ndarray)
+            and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
+        # position -> corpus id on the device, before the copy back (same values as :183)
+        topk_scores, topk_ids = index.search(query_embeds, topk, corpus_ids=corpus_ids)
+    else:
+        topk_scores, topk_idx = index.search(query_embeds, topk)
+        topk_ids = corpus_ids[topk_idx]      # == np.vstack([corpus_ids[x] for x in topk_idx]) (:183)
     assert len(query_ids) == len(topk_scores) == len(topk_ids)
     return topk_scores, topk_ids
 
@@ -84,6 +89,8 @@ def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np
         topk_scores, topk_ids = search(query_id_iter, query_embeds_iter, corpus_ids, index, topk)
         all_topk_scores.append(topk_scores)
         all_topk_ids.append(topk_ids)
+    if len(all_topk_scores) == 1:            # one batch: concatenate would only copy
+        return all_topk_scores[0], all_topk_ids[0]
     all_topk_scores = np.concatenate(all_topk_scores, axis=0)
     all_topk_ids = np.concatenate(all_topk_ids, axis=0)
     return all_topk_scores, all_topk_ids

@@ -166,6 +166,7 @@ class GpuIndexPQ:
         self.is_trained = True
         self._ws = None
         self._stage = {}
+        self._ids_cache = {}
         self.last_stats = None
 
     @classmethod
@@ -228,7 +229,21 @@ class GpuIndexPQ:
             self._stage[name] = buf
         return buf[:n].view(shape)
 
-    def search(self, x, k):
+    def _resident_ids(self, corpus_ids):
+        """device copy of an external id table, cached per host array (pointer, length, dtype)"""
+        a = np.ascontiguousarray(corpus_ids)
+        if a.dtype != np.int64:
+            return None
+        # pointer + shape + a strided 1024-element fingerprint (catches in-place edits of the table)
+        key = (a.__array_interface__["data"][0], a.shape, hash(a[:: max(1, a.size // 1024)].tobytes()))
+        hit = self._ids_cache.get("key")
+        if hit != key:
+            self._ids_cache = {"key": key, "dev": torch.from_numpy(a).to(self.device), "ref": a}
+        return self._ids_cache["dev"]
+
+    def search(self, x, k, corpus_ids=None):
+        """Faiss `index.search(x, k)`.  With `corpus_ids` (int64 array) the returned ids are
+        `corpus_ids[position]`, mapped on the device before the copy back (evaluate_repconc.py:183)."""
         if isinstance(x, torch.Tensor):
             if not x.is_cuda:
                 x = x.to(self.device)
@@ -243,6 +258,12 @@ class GpuIndexPQ:
             hx = self._pinned("x", x.shape, torch.float32)
             hx.copy_(torch.from_numpy(x))
             s, i = self.search_tensor(hx.to(self.device, non_blocking=True), k)
+            ids_dev = self._resident_ids(corpus_ids) if corpus_ids is not None else None
+            if ids_dev is not None:
+                mapped = torch.empty_like(i)
+                _lib.check(_lib.load().rc_map_ids(i.data_ptr(), ids_dev.data_ptr(), ids_dev.numel(), i.numel(),
+                                                  mapped.data_ptr(), ops._stream()), "rc_map_ids")
+                i = mapped
             hs = self._pinned("s", (nq, k), torch.float32)
             hi = self._pinned("i", (nq, k), torch.int64)
             hs.copy_(s, non_blocking=True)

@@ -186,3 +186,19 @@ def test_shard_merge(oracle):
     ms, mi = E.merge_shard_results(torch.stack(ss), torch.stack(ii))
     os_, oi = oracle.adc_search(q, c, codes, k)
     assert np.array_equal(ms.cpu().numpy(), os_) and np.array_equal(mi.cpu().numpy(), oi)
+
+
+def test_map_ids_on_device_matches_numpy_indexing():
+    """search(..., corpus_ids) maps positions to external ids on the device exactly like the reference's
+    `corpus_ids[x]` (evaluate_repconc.py:183), including the -1 padding wrapping to corpus_ids[-1]."""
+    from repconc_b200 import evaluate_repconc as E
+    case = dict(GC.ADC_CASES["adc_m8"], N=37, nq=3)
+    q, c, codes = GC.adc_inputs(case)
+    idx = _index(c, codes)
+    corpus_ids = (np.arange(37, dtype=np.int64) * 7 + 1000)
+    s_pos, i_pos = idx.search(q, 50)                       # positions, padded with -1 beyond N
+    s_map, i_map = E.search(np.arange(3), q, corpus_ids, idx, 50)
+    assert np.array_equal(s_map, s_pos) and np.array_equal(i_map, corpus_ids[i_pos])
+    corpus_ids[5] = -42                                     # in-place edit must not hit a stale device copy
+    _, i_map2 = E.search(np.arange(3), q, corpus_ids, idx, 50)
+    assert np.array_equal(i_map2, corpus_ids[i_pos])

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Small end-to-end pass over every kernel for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from repconc_b200 import ops, sinkhorn_algorithm
+from repconc_b200.faiss_compat import GpuIndexPQ
+gen = torch.Generator(device="cuda").manual_seed(0)
+for (B, M, K, ds, T) in [(300, 4, 256, 16, 12), (70, 3, 64, 5, 4), (513, 2, 256, 8, 12)]:
+    x = torch.randn((B, M * ds), generator=gen, device="cuda")
+    c = torch.randn((M, K, ds), generator=gen, device="cuda", requires_grad=True)
+    for dense in (False, True):
+        from repconc_b200 import _lib
+        prev = _lib.load().rc_sinkhorn_set_dense(1 if dense else 0)
+        codes = ops.constrained_assign(x, c, 0.003, T, distributed=False)
+        _lib.load().rc_sinkhorn_set_dense(prev)
+    nn = ops.nn_assign(x, c, uint8=(K <= 256))
+    xg = x.clone().requires_grad_(True)
+    g = torch.randn_like(x) / B
+    mse, sur = ops.quantization_loss(xg, c, codes, g, 1e-4)
+    (mse + sur).backward()
+    q = ops.decode(codes, c)
+    q.sum().backward()
+M, ds = 16, 4
+c = torch.randn((M, 256, ds), generator=gen, device="cuda")
+for N, nq, k in [(3000, 9, 17), (300_000, 20, 100)]:
+    codes = torch.randint(0, 256, (N, M), generator=gen, device="cuda", dtype=torch.uint8)
+    qv = torch.randn((nq, M * ds), generator=gen, device="cuda")
+    s, i = GpuIndexPQ(codes, c).search_tensor(qv, k)
+torch.cuda.synchronize()
+print("sanitize_smoke done", float(s.sum()))
