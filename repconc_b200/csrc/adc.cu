@@ -274,6 +274,11 @@ struct PackScanArgs {
     unsigned int* cnt;       // (nq)
     uint32_t* cand;          // (nq, cap) document positions
     int cap;
+    // sample mode of adc_scan_cf_kernel<MT, true>: position p -> document (p / blk) * stride + p % blk,
+    // integer sums written densely: out16[q * ld16 + p]
+    int64_t blk, stride;
+    uint16_t* out16;
+    int64_t ld16;
 };
 
 template <int QP, int MT>
@@ -358,7 +363,7 @@ adc_scan_packed_kernel(PackScanArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int CF_THREADS = 1024;   // 32 warps: the gathers are latency-bound at 16
 
-template <int MT>
+template <int MT, bool SAMPLE>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 adc_scan_cf_kernel(PackScanArgs a) {
     static_assert(MT % 8 == 0, "8 consecutive sub-vectors per quarter-warp");
@@ -380,7 +385,7 @@ adc_scan_cf_kernel(PackScanArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = lane & 7, sub = lane >> 3;
     const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0;
-    const int my_thr = j < nqt ? a.thr_i[q0 + j] : 0x7fffffff;   // lane j of a quarter owns query j
+    const int my_thr = (!SAMPLE && j < nqt) ? a.thr_i[q0 + j] : 0x7fffffff;   // lane j of a quarter owns query j
     __syncthreads();
 
     const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
@@ -404,17 +409,24 @@ adc_scan_cf_kernel(PackScanArgs a) {
         uint32_t w = (b1 ? k1 : k0) + r2;
         w += __shfl_xor_sync(0xffffffffu, w, 1);
         const int sum = (int)((w >> (16 * (j & 1))) & 0xffffu);
-        if (live && sum >= my_thr) {
+        if (SAMPLE) {
+            if (live && j < nqt) a.out16[(q0 + j) * a.ld16 + p] = (uint16_t)sum;
+        } else if (live && sum >= my_thr) {
             const unsigned int pos = atomicAdd(a.cnt + q0 + j, 1u);
             if (pos < (unsigned int)a.cap) a.cand[(q0 + j) * (int64_t)a.cap + pos] = (uint32_t)p;
         }
+    };
+    // position -> first code byte of this lane (sample mode scans evenly spaced blocks of the corpus)
+    auto code_ptr = [&](int64_t pos) {
+        const int64_t doc = SAMPLE ? (pos / a.blk) * a.stride + (pos % a.blk) : pos;
+        return a.codes + doc * MT + j;
     };
 
     // full iterations (every document of every warp's group is inside the split): no predicates, code bytes
     // of the next group are loaded while this one is scanned
     const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
     int64_t p = p_lo + warp * 4 + sub;
-    const uint8_t* cp = a.codes + p * MT + j;
+    const uint8_t* cp = code_ptr(p);
     uint32_t cb[MT / 8], cn[MT / 8];
     if (full > 0) {
 #pragma unroll
@@ -422,8 +434,9 @@ adc_scan_cf_kernel(PackScanArgs a) {
     }
     for (int64_t t = 0; t < full; ++t) {
         if (t + 1 < full) {
+            const uint8_t* cq = SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT;
 #pragma unroll
-            for (int i = 0; i < MT / 8; ++i) cn[i] = __ldg(cp + (int64_t)DOCS_PER_IT * MT + 8 * i);
+            for (int i = 0; i < MT / 8; ++i) cn[i] = __ldg(cq + 8 * i);
         }
         scan_group(cb, p, true);
 #pragma unroll
@@ -431,18 +444,19 @@ adc_scan_cf_kernel(PackScanArgs a) {
         p += DOCS_PER_IT;
         cp += (int64_t)DOCS_PER_IT * MT;
     }
-    // tail: fewer than 64 documents left in the split
+    // tail: fewer than DOCS_PER_IT documents left in the split
     if (p_lo + full * DOCS_PER_IT < p_hi) {   // block-uniform
         const bool live = p < p_hi;
+        const uint8_t* ct = live ? code_ptr(p) : a.codes + j;
 #pragma unroll
-        for (int i = 0; i < MT / 8; ++i) cb[i] = live ? (uint32_t)__ldg(cp + 8 * i) : 0u;
+        for (int i = 0; i < MT / 8; ++i) cb[i] = live ? (uint32_t)__ldg(ct + 8 * i) : 0u;
         scan_group(cb, p, live);
     }
 }
 
-template <int MT>
+template <int MT, bool SAMPLE = false>
 static int launch_cf_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
-    auto kern = adc_scan_cf_kernel<MT>;
+    auto kern = adc_scan_cf_kernel<MT, SAMPLE>;
     const size_t smem = (size_t)MT * ADC_K * 16;
     static bool attr_done = false;
     if (!attr_done) {
@@ -453,6 +467,71 @@ static int launch_cf_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
     kern<<<grid, CF_THREADS, smem, st>>>(a);
     RC_CHECK_LAUNCH("adc_scan_cf_kernel");
     return RC_OK;
+}
+
+// r-th largest 16-bit integer sum of a sample row (2 radix passes); the filter threshold of the packed scan
+__global__ void __launch_bounds__(SEL_THREADS)
+radix_select_u16_kernel(const uint16_t* __restrict__ dense, int64_t ld, int64_t n, int rank, int* __restrict__ thr_i) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_hi, s_rem;
+    const int64_t q = blockIdx.x;
+    const uint16_t* row = dense + q * ld;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < n; i += SEL_THREADS) atomicAdd(&hist[row[i] >> 8], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int cum = 0;
+        int b = 255;
+        for (; b > 0; --b) {
+            if (cum + hist[b] >= (unsigned int)rank) break;
+            cum += hist[b];
+        }
+        s_hi = (unsigned int)b;
+        s_rem = (unsigned int)rank - cum;
+    }
+    __syncthreads();
+    const unsigned int hi = s_hi;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < n; i += SEL_THREADS) {
+        const unsigned int v = row[i];
+        if ((v >> 8) == hi) atomicAdd(&hist[v & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int cum = 0;
+        int b = 255;
+        for (; b > 0; --b) {
+            if (cum + hist[b] >= s_rem) break;
+            cum += hist[b];
+        }
+        thr_i[q] = (int)((hi << 8) | (unsigned int)b);
+    }
+}
+
+static void scan_splits(int64_t nq, int qt, int64_t npos, int M, int64_t* pps_out, int64_t* splits_out);
+
+// true when the conflict-free kernel (and with it the integer-domain sampling) serves this M
+static bool cf_capable(int M) { return M % 8 == 0 && M >= 8 && M <= 48; }
+
+static int launch_cf_sample(PackScanArgs a, cudaStream_t st) {
+    int64_t pps, splits;
+    scan_splits(a.nq, 8, a.npos, a.M, &pps, &splits);
+    pps = (pps + 127) / 128 * 128;
+    splits = (a.npos + pps - 1) / pps;
+    a.pos_per_split = pps;
+    switch (a.M) {
+        case 8: return launch_cf_inst<8, true>(a, (int)splits, st);
+        case 16: return launch_cf_inst<16, true>(a, (int)splits, st);
+        case 24: return launch_cf_inst<24, true>(a, (int)splits, st);
+        case 32: return launch_cf_inst<32, true>(a, (int)splits, st);
+        case 40: return launch_cf_inst<40, true>(a, (int)splits, st);
+        case 48: return launch_cf_inst<48, true>(a, (int)splits, st);
+        default: break;
+    }
+    set_error("launch_cf_sample: unsupported M=%d", a.M);
+    return RC_E_UNSUPPORTED;
 }
 
 static int scan_qp(int M) {
@@ -767,7 +846,9 @@ sort_candidates_kernel(const unsigned long long* __restrict__ cand, int cap, con
 // status: 0 ok, 1 fewer than k_eff exact survivors, 2 the approximate list overflowed, 3 too many survivors
 __global__ void __launch_bounds__(SEL_THREADS)
 adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict__ codes, int M,
-                        const float* __restrict__ thr, const uint32_t* __restrict__ cand, int cap,
+                        const float* __restrict__ thr, const int* __restrict__ thr_i,
+                        const float* __restrict__ qstep, const double* __restrict__ qsumlo,
+                        const double* __restrict__ qsumabs, const uint32_t* __restrict__ cand, int cap,
                         const unsigned int* __restrict__ cnt, int k, int k_eff, int64_t id_offset,
                         float* __restrict__ scores, int64_t ld_s, int64_t* __restrict__ ids, int64_t ld_i,
                         int* __restrict__ status, unsigned int* __restrict__ exact_cnt) {
@@ -782,7 +863,10 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const float* t = lut + q * (int64_t)M * ADC_K;
-    const float tau = thr[q];
+    // thr != NULL : exact fp32 threshold known (fp32 sampling) -> keep score >= tau
+    // thr == NULL : only the integer threshold T is known (integer-domain sampling) -> keep everything and
+    //               verify afterwards that the k-th kept score beats every document the scan left out
+    const float tau = thr ? thr[q] : -FLT_MAX;
     const uint32_t* src = cand + q * (int64_t)cap;
     for (unsigned int i = threadIdx.x; i < c_approx; i += SEL_THREADS) {
         const uint32_t doc = src[i];
@@ -813,6 +897,19 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
     while (n < (int)c) n <<= 1;
     for (int i = (int)c + threadIdx.x; i < n; i += SEL_THREADS) skeys[i] = 0ull;
     bitonic_sort_desc(skeys, n);
+    if (!thr) {
+        // a document the scan left out has integer sum <= T - 1, hence (quantisation bound, see
+        // adc_int_threshold_kernel) exact score <= sumlo + step * (T - 1 + 0.501 M + slack): the result is
+        // exact iff the k-th kept score is strictly above that
+        const double st = (double)qstep[q];
+        const double slack = (double)M * 1.2e-7 * qsumabs[q] / st + 1.0;
+        const double ub = qsumlo[q] + st * ((double)thr_i[q] - 1.0 + (double)M * 0.501 + slack);
+        const float sk = key_to_f32((uint32_t)(skeys[k_eff - 1] >> 32));
+        if (!((double)sk > ub)) {
+            if (threadIdx.x == 0) status[q] = 1;
+            return;
+        }
+    }
     for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
         if (i < k_eff) {
             const unsigned long long key = skeys[i];
@@ -1106,8 +1203,26 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             g_stats[1] += qc;
             continue;
         }
+        const int qmax = 65535 / M;
+        adc_quantise_lut_kernel<<<(unsigned)qc, ADC_K, (size_t)M * 4, st>>>(w.lut, M, qmax, w.qlut, w.qstep, w.qsumlo,
+                                                                          w.qsumabs);
+        RC_CHECK_LAUNCH("adc_quantise_lut_kernel");
+        const bool int_sampling = cf_capable(M) && !adc_force_gather();
         // 1. thresholds from a strided sample of the corpus
-        {
+        if (int_sampling) {
+            // integer domain: the sample is scanned by the packed kernel itself and the threshold is the
+            // r-th largest 16-bit sum (exactness is verified after the re-score, adc_rescore_sort_kernel)
+            PackScanArgs a{};
+            a.qlut = w.qlut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.M = M;
+            a.blk = SAMPLE_BLK; a.stride = p.stride; a.out16 = reinterpret_cast<uint16_t*>(w.dense);
+            a.ld16 = p.n_sample;
+            rc = launch_cf_sample(a, st);
+            if (rc) return rc;
+            radix_select_u16_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(reinterpret_cast<uint16_t*>(w.dense),
+                                                                           p.n_sample, p.n_sample, p.rank_sample,
+                                                                           w.thr_i);
+            RC_CHECK_LAUNCH("radix_select_u16_kernel");
+        } else {
             ScanArgs a{};
             a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.blk = SAMPLE_BLK; a.stride = p.stride;
             a.M = M; a.out = w.dense; a.ld_out = p.n_sample;
@@ -1116,17 +1231,13 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             radix_select_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(w.dense, p.n_sample, p.n_sample, nullptr,
                                                                        p.rank_sample, nullptr, w.thr, nullptr);
             RC_CHECK_LAUNCH("radix_select_kernel");
-        }
-        // 2. packed integer filter scan of the whole corpus (thresholds lowered by the quantisation bound)
-        RC_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)qc * 4, st));
-        {
-            const int qmax = 65535 / M;
-            adc_quantise_lut_kernel<<<(unsigned)qc, ADC_K, (size_t)M * 4, st>>>(w.lut, M, qmax, w.qlut, w.qstep,
-                                                                              w.qsumlo, w.qsumabs);
-            RC_CHECK_LAUNCH("adc_quantise_lut_kernel");
             adc_int_threshold_kernel<<<(unsigned)((qc + 255) / 256), 256, 0, st>>>(w.thr, w.qstep, w.qsumlo,
                                                                                    w.qsumabs, M, qc, w.thr_i);
             RC_CHECK_LAUNCH("adc_int_threshold_kernel");
+        }
+        // 2. packed integer filter scan of the whole corpus
+        RC_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)qc * 4, st));
+        {
             PackScanArgs a{};
             a.qlut = w.qlut; a.codes = codes; a.thr_i = w.thr_i; a.nq = qc; a.npos = N; a.M = M;
             a.cnt = w.cnt; a.cand = w.cand32; a.cap = CAND_CAP;
@@ -1137,8 +1248,8 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         }
         // 3. exact re-score of the survivors + per-query sort
         adc_rescore_sort_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
-            w.lut, codes, M, w.thr, w.cand32, CAND_CAP, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k,
-            ids + c0 * k, k, w.status, w.exact_cnt);
+            w.lut, codes, M, int_sampling ? nullptr : w.thr, w.thr_i, w.qstep, w.qsumlo, w.qsumabs, w.cand32, CAND_CAP,
+            w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status, w.exact_cnt);
         RC_CHECK_LAUNCH("adc_rescore_sort_kernel");
         // 4. queries whose list under/overflowed take the exact dense path
         status_h.resize(qc);
