@@ -185,6 +185,20 @@ class GpuIndexPQ:
     def device(self):
         return self.codes.device
 
+    def add(self, new_codes):
+        """Append (n, M) uint8 codes that are already on the device (the GPU-side `add_docs`: corpus
+        encoding with `ops.nn_assign(..., uint8=True)` never has to leave HBM).  Amortised growth."""
+        ops._require_cuda(new_codes, "new_codes")
+        assert new_codes.dtype == torch.uint8 and new_codes.dim() == 2 and new_codes.shape[1] == self.M
+        n_old, n_new = self.ntotal, int(new_codes.shape[0])
+        cap = getattr(self, "_cap", None)
+        if cap is None or cap.shape[0] < n_old + n_new or cap.data_ptr() != self.codes.data_ptr():
+            cap = torch.empty((max(2 * n_old, n_old + n_new), self.M), dtype=torch.uint8, device=self.device)
+            cap[:n_old] = self.codes
+            self._cap = cap
+        cap[n_old:n_old + n_new] = new_codes.to(self.device)
+        self.codes = cap[: n_old + n_new]
+
     def set_centroids(self, centroids):
         with torch.no_grad():
             self.centroids.copy_(centroids.detach().reshape(self.centroids.shape))

@@ -202,3 +202,65 @@ def test_map_ids_on_device_matches_numpy_indexing():
     corpus_ids[5] = -42                                     # in-place edit must not hit a stale device copy
     _, i_map2 = E.search(np.arange(3), q, corpus_ids, idx, 50)
     assert np.array_equal(i_map2, corpus_ids[i_pos])
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (8,841,823 docs, M=48, k=1000): size-independent properties --
+    sorted descending, ids unique and in range, every returned score equals an independent dense
+    re-computation, the k-th score is the true k-th largest of the whole corpus, sharded == unsharded,
+    and the search is idempotent."""
+    from repconc_b200 import _lib, ops
+    from repconc_b200 import evaluate_repconc as E
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    lib = _lib.load()
+    N, M, ds, nq, k = 8_841_823, 48, 16, 64, 1000
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    codes = torch.randint(0, 256, (N, M), generator=gen, device="cuda", dtype=torch.uint8)
+    c = torch.randn((M, 256, ds), generator=gen, device="cuda")
+    q = torch.randn((nq, M * ds), generator=gen, device="cuda")
+    idx = GpuIndexPQ(codes, c)
+    s, i = idx.search_tensor(q, k)
+    assert idx.last_stats["filtered"] == nq and idx.last_stats["dense"] == 0
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    assert int(i.min()) >= 0 and int(i.max()) < N
+    assert all(len(torch.unique(i[r])) == k for r in range(nq))
+    # dense fp32 scores of 4 queries over the whole corpus through the un-quantised scan kernel
+    lut = torch.empty((4, M, 256), device="cuda")
+    _lib.check(lib.rc_adc_lut(q.data_ptr(), q.stride(0), c.data_ptr(), 4, M, 256, ds, lut.data_ptr(), ops._stream()),
+               "lut")
+    dense = torch.empty((4, N), device="cuda")
+    _lib.check(lib.rc_adc_scores(lut.data_ptr(), codes.data_ptr(), 4, 0, N, M, dense.data_ptr(), ops._stream()),
+               "scores")
+    assert torch.equal(torch.gather(dense, 1, i[:4]), s[:4])            # bit-exact scores
+    top = torch.topk(dense, k, dim=1).values
+    assert torch.equal(top, s[:4])                                      # the true top-k score multiset
+    # 3 shards merged == unsharded
+    parts = []
+    for w in range(3):
+        lo, hi = E.shard_bounds(N, w, 3)
+        parts.append(GpuIndexPQ(codes[lo:hi], c, id_offset=lo).search_tensor(q, k))
+    ms, mi = E.merge_shard_results(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(ms, s) and torch.equal(mi, i)
+    s2, i2 = idx.search_tensor(q, k)
+    assert torch.equal(s2, s) and torch.equal(i2, i)
+
+
+def test_gpu_side_add_and_centroid_refresh(oracle):
+    """Device-side append of codes (corpus encoding never leaves HBM) and the in-place centroid refresh
+    that replaces JPQ's per-step index re-clone (finetune_jpq.py:208-214)."""
+    from repconc_b200 import ops
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    case = GC.ADC_CASES["adc_m8"]
+    q, c, codes = GC.adc_inputs(case)
+    idx = GpuIndexPQ(_dev(codes[:100]), _dev(c))
+    for lo in range(100, len(codes), 3300):
+        idx.add(_dev(codes[lo:lo + 3300]))
+    assert idx.ntotal == len(codes)
+    s, i = idx.search(q, 10)
+    os_, oi = oracle.adc_search(q, c, codes, 10)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi)
+    c2 = (c * 1.5 + 0.25).astype(np.float32)
+    idx.set_centroids(_dev(c2))
+    s2, i2 = idx.search(q, 10)
+    o2 = oracle.adc_search(q, c2, codes, 10)
+    assert np.array_equal(s2, o2[0]) and np.array_equal(i2, o2[1])
