@@ -35,7 +35,8 @@ extern "C" {
 #define RC_FLAG_NONFINITE 1 /* Q would hold NaN/Inf: models/repconc/modeling_repconc.py:64-65 */
 #define RC_FLAG_AMPLITUDE 2 /* `assert torch.all(amplitude > 0)` would fire: modeling_repconc.py:83 */
 #define RC_FLAG_BADCODE 4   /* rc_decode saw a code outside [0, K) */
-#define RC_FLAG_SPARSE_UNSAFE 8 /* a row kept < 2^-12/K of mass: re-run with rc_sinkhorn_set_dense(1) */
+#define RC_FLAG_SPARSE_UNSAFE 8 /* a row kept < 2^-8/K of mass: re-run with rc_sinkhorn_set_dense(1) */
+#define RC_FLAG_PEER_TIMEOUT 16 /* rc_peer_allreduce_f64: a peer never signalled (bounded spin expired) */
 
 const char* rc_last_error(void);
 /* library / build identification: "repconc_b200 <version> sm_100a" */
@@ -115,6 +116,20 @@ int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, i
 int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One-shot all-reduce (SUM, fp64, in place) of the row sums over NVLink peer memory: the
+ * `dist.all_reduce(sum_of_rows)` of modeling_repconc.py:156-157 without NCCL.
+ *   peer_buffers_host  HOST array of W device pointers: rank p's symmetric buffer as mapped into THIS
+ *                      process (rc_peer_allreduce_buffer_bytes(n) bytes each, zero-initialised once,
+ *                      e.g. torch.distributed._symmetric_memory buffers)
+ *   seq                1, 2, 3, ... -- the same value on every rank for the same exchange
+ *   flags              RC_FLAG_PEER_TIMEOUT is OR-ed in if a peer never arrives (the result is then undefined)
+ * Every rank sums the W vectors in rank order, so all ranks hold bitwise identical results.
+ * ------------------------------------------------------------------------------------------- */
+size_t rc_peer_allreduce_buffer_bytes(int64_t n);
+int rc_peer_allreduce_f64(const uint64_t* peer_buffers_host, int rank, int W, int64_t n, uint32_t seq,
+                          double* inout, int32_t* flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a6  decode: q[b, m*ds:(m+1)*ds] = c[m, codes[b,m], :]        (modeling_repconc.py:168-184)

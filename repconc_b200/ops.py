@@ -18,6 +18,7 @@ FLAG_NONFINITE = 1
 FLAG_AMPLITUDE = 2
 FLAG_BADCODE = 4
 FLAG_SPARSE_UNSAFE = 8
+FLAG_PEER_TIMEOUT = 16
 
 
 def _stream():
@@ -186,12 +187,24 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
         minmax[1].neg_()
     B_global = kern.B * world
     P = kern.begin(eps)
+    # row-sum exchange: one-shot NVLink peer-memory all-reduce when available, NCCL otherwise
+    reducer = None
+    if distributed and isinstance(P, torch.Tensor) and P.is_cuda:
+        from .peer import PeerAllReduce
+        reducer = PeerAllReduce.get(P.numel(), P.device, group)
+
+    def sum_rows(P):
+        if reducer is not None:
+            reducer.all_reduce(P, kern.flags)
+        else:
+            dist.all_reduce(P, dist.ReduceOp.SUM, group=group)
+
     for _ in range(max(int(iters) - 1, 0)):
         if distributed:
-            dist.all_reduce(P, dist.ReduceOp.SUM, group=group)
+            sum_rows(P)
         P = kern.step(eps, B_global)
     if distributed and iters >= 1:
-        dist.all_reduce(P, dist.ReduceOp.SUM, group=group)
+        sum_rows(P)
     codes = kern.finish(eps, iters >= 1, uint8=uint8, B_global=B_global)
     flags = kern.read_flags()
     if flags & FLAG_SPARSE_UNSAFE and not _retry_dense:
@@ -203,6 +216,8 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
             return constrained_assign_driver(kern, eps, iters, distributed, group, uint8, _retry_dense=True)
         finally:
             kern.set_dense(prev)
+    if flags & FLAG_PEER_TIMEOUT:
+        raise _lib.RepconcLibraryError("peer all-reduce timed out: a rank never reached the exchange")
     if flags & FLAG_AMPLITUDE:
         raise AssertionError("amplitude > 0 (center_distance_for_constraint)")
     if flags & FLAG_NONFINITE:

@@ -58,10 +58,30 @@ def main():
     so, io = O.adc_search(q, cc, codes_h, 100)
     s_ok = bool(np.array_equal(s.cpu().numpy(), so) and np.array_equal(i.cpu().numpy(), io))
     ok &= s_ok
+    # --- peer-memory all-reduce (rc_peer_allreduce_f64) vs a rank-ordered sum of all-gathered vectors
+    from repconc_b200.peer import PeerAllReduce
+    n = 48 * 256
+    red = PeerAllReduce.get(n, dev)
+    p_ok, p_used = True, red is not None
+    if red is not None:
+        fl = torch.zeros(1, dtype=torch.int32, device=dev)
+        for it in range(5):
+            g = torch.Generator(device=dev).manual_seed(100 * it + rank)
+            v = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (10.0 ** (rank - it))
+            allv = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+            want = allv[0].clone()
+            for r in range(1, world):
+                want += allv[r]
+            red.all_reduce(v, fl)
+            p_ok = p_ok and bool(torch.equal(v, want))
+        p_ok = p_ok and int(fl.item()) == 0
+    ok &= p_ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, dist.ReduceOp.MIN)
     if rank == 0:
         print(f"dist_check world={world}: assign_golden={a_ok} assign_global_batch={b_ok} sharded_adc={s_ok} "
+              f"peer_allreduce={'exact' if (p_used and p_ok) else ('MISMATCH' if p_used else 'unavailable (NCCL used)')} "
               f"-> {'PASS' if flag.item() == 1 else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
