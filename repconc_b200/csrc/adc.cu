@@ -7,19 +7,22 @@
 //           `add_docs` input; a document is M consecutive bytes (48 B at M = 48)
 //   lut     (nq, M, 256) fp32, <x_q[m,:], c[m,k,:]>
 //   scores  never materialised for the full corpus: the scan keeps, per query, only documents whose
-//           score reaches a threshold estimated from a strided sample of the corpus
+//           (quantised) score reaches a threshold taken from a strided sample of the corpus; survivors
+//           are re-scored exactly
 //
-// Kernels
-//   adc_lut_kernel      inner-product tables
-//   adc_scan_kernel     the hot loop.  One CTA holds the LUTs of QT queries interleaved in shared
-//                       memory ([m][k][QT], one LDS.128 serves 4 queries), one thread owns one
-//                       document: its M code bytes are loaded once (vectorised, coalesced) into
-//                       registers and reused for the QT queries; accumulation is fp32, m ascending
-//                       (bit-identical to a sequential CPU scan).  Epilogue either stores dense
-//                       scores (sample / small corpora / exact fallback) or appends (score, id) to the
-//                       query's candidate list when score >= threshold.
-//   select/gather/sort  exact top-k: 4-pass radix select over fp32 keys, tie-exact ordered gather,
-//                       bitonic sort of <= 8192 composite keys (score desc, id asc).
+// Kernels (details at each definition)
+//   adc_lut_kernel            fp32 inner-product tables
+//   adc_quantise_lut_kernel   per-query integer tables (uint16, two queries per 32-bit word)
+//   adc_scan_cf_kernel        THE HOT LOOP: bank-conflict-free packed-integer filter scan, 8 queries per
+//                             16-byte shared-memory entry, a quarter-warp per document; also scans the
+//                             threshold sample (16-bit sums out)
+//   adc_scan_packed_kernel    same arithmetic, thread-per-document gather (M not a multiple of 8, M > 48)
+//   adc_scan_kernel           un-quantised fp32 scan with dense score output (small corpora, exact fallback,
+//                             fp32 sampling for the gather variant); accumulation fp32, m ascending =
+//                             bit-identical to a sequential CPU scan
+//   radix_select_*            r-th largest of a sample row (16-bit integer sums / fp32 keys)
+//   adc_rescore_sort_kernel   exact fp32 re-score of the filter's survivors + bitonic sort + exactness check
+//   gather_topk / sort_candidates / topk_merge   tie-exact dense top-k, per-shard list merge
 #include <float.h>
 #include <stdlib.h>
 
@@ -84,17 +87,14 @@ struct ScanArgs {
     int64_t blk, stride;     // blk == 0: doc = n0 + pos ; else doc = (pos / blk) * stride + pos % blk
     int64_t n0;
     int M;
-    // dense epilogue
-    float* out; int64_t ld_out;
-    // filter epilogue
-    const float* thr; unsigned int* cnt; unsigned long long* cand; int cap;
+    float* out; int64_t ld_out;   // dense scores: out[q * ld_out + pos]
 };
 
 __device__ __forceinline__ unsigned long long pack_cand(float score, uint32_t doc) {
     return ((unsigned long long)f32_to_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
 }
 
-template <int QT, int MT, bool FILTER>
+template <int QT, int MT>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 adc_scan_kernel(ScanArgs a) {
     using V = typename LutVec<QT>::type;
@@ -113,9 +113,6 @@ adc_scan_kernel(ScanArgs a) {
             for (int i = threadIdx.x; i < n; i += SCAN_THREADS) lf[i * QT + qq] = qq < nqt ? __ldg(src + i) : 0.0f;
         }
     }
-    float thr[QT];
-#pragma unroll
-    for (int qq = 0; qq < QT; ++qq) thr[qq] = (FILTER && qq < nqt) ? a.thr[q0 + qq] : 0.0f;
     __syncthreads();
 
     const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
@@ -156,20 +153,10 @@ adc_scan_kernel(ScanArgs a) {
         } else {
             for (int m = 0; m < M; ++m) lut_add<QT>(acc, lutS[m * ADC_K + __ldg(cp + m)]);
         }
-        if constexpr (FILTER) {
 #pragma unroll
-            for (int qq = 0; qq < QT; ++qq) {
-                if (qq < nqt && acc[qq] >= thr[qq]) {
-                    const unsigned int pos = atomicAdd(a.cnt + q0 + qq, 1u);
-                    if (pos < (unsigned int)a.cap)
-                        a.cand[(q0 + qq) * (int64_t)a.cap + pos] = pack_cand(acc[qq], (uint32_t)doc);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int qq = 0; qq < QT; ++qq)
-                if (qq < nqt) a.out[(q0 + qq) * a.ld_out + p] = acc[qq];
-        }
+        for (int qq = 0; qq < QT; ++qq)
+            if (qq < nqt) a.out[(q0 + qq) * a.ld_out + p] = acc[qq];
+
     }
 }
 
@@ -637,9 +624,9 @@ static int scan_qt(int M) {
     return 0;
 }
 
-template <int QT, int MT, bool FILTER>
+template <int QT, int MT>
 static int launch_scan_inst(const ScanArgs& a, int splits, cudaStream_t st) {
-    auto kern = adc_scan_kernel<QT, MT, FILTER>;
+    auto kern = adc_scan_kernel<QT, MT>;
     const size_t smem = (size_t)a.M * ADC_K * 4 * QT;
     static bool attr_done = false;
     if (!attr_done) {
@@ -652,7 +639,6 @@ static int launch_scan_inst(const ScanArgs& a, int splits, cudaStream_t st) {
     return RC_OK;
 }
 
-template <bool FILTER>
 static int launch_scan(ScanArgs a, cudaStream_t st) {
     if (a.nq <= 0 || a.npos <= 0) return RC_OK;
     const int qt = scan_qt(a.M);
@@ -674,7 +660,7 @@ static int launch_scan(ScanArgs a, cudaStream_t st) {
         splits = (a.npos + pps - 1) / pps;
     }
     a.pos_per_split = pps;
-#define RC_SCAN(QT, MT) return launch_scan_inst<QT, MT, FILTER>(a, (int)splits, st)
+#define RC_SCAN(QT, MT) return launch_scan_inst<QT, MT>(a, (int)splits, st)
     if (qt == 4) {
         switch (a.M) {
             case 8: RC_SCAN(4, 8);
@@ -1125,7 +1111,7 @@ RC_API int rc_adc_scores(const float* lut, const uint8_t* codes, int64_t nq, int
     ScanArgs a{};
     a.lut = lut; a.codes = codes; a.nq = nq; a.npos = n; a.blk = 0; a.stride = 0; a.n0 = n0; a.M = M;
     a.out = out; a.ld_out = n;
-    return launch_scan<false>(a, (cudaStream_t)stream);
+    return launch_scan(a, (cudaStream_t)stream);
 }
 
 RC_API size_t rc_adc_search_workspace_bytes(int64_t nq, int64_t N, int M, int K, int64_t k) {
@@ -1195,7 +1181,7 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
                 ScanArgs a{};
                 a.lut = w.lut + r0 * (int64_t)M * ADC_K; a.codes = codes; a.nq = rows; a.npos = N; a.n0 = 0; a.M = M;
                 a.out = w.dense; a.ld_out = N;
-                rc = launch_scan<false>(a, st);
+                rc = launch_scan(a, st);
                 if (rc) return rc;
                 rc = dense_topk(w, rows, N, ik, p.k_eff, id_offset, scores + (c0 + r0) * k, k, ids + (c0 + r0) * k, k, st);
                 if (rc) return rc;
@@ -1226,7 +1212,7 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             ScanArgs a{};
             a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.blk = SAMPLE_BLK; a.stride = p.stride;
             a.M = M; a.out = w.dense; a.ld_out = p.n_sample;
-            rc = launch_scan<false>(a, st);
+            rc = launch_scan(a, st);
             if (rc) return rc;
             radix_select_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(w.dense, p.n_sample, p.n_sample, nullptr,
                                                                        p.rank_sample, nullptr, w.thr, nullptr);
@@ -1278,7 +1264,7 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             ScanArgs a{};
             a.lut = w.fb_lut; a.codes = codes; a.nq = rows; a.npos = N; a.n0 = 0; a.M = M;
             a.out = w.dense; a.ld_out = N;
-            rc = launch_scan<false>(a, st);
+            rc = launch_scan(a, st);
             if (rc) return rc;
             rc = dense_topk(w, rows, N, ik, p.k_eff, id_offset, w.fb_scores, k, w.fb_ids, k, st);
             if (rc) return rc;

@@ -6,14 +6,23 @@
 //   centroids  (M, K, ds) fp32                               nn.Parameter of the module
 //   table      (M, B, K) fp32, k fastest                     raw distances, centred IN PLACE by
 //                                                            rc_sinkhorn_begin (never widened to fp64)
-//   state      lu (M,K) f64 | P (M,K) f64 | lv (M,B) f64 | partial (G, S, K) f64
+//   state      lu, lu_build, U (M,K) f64 | P (M,K) f64 (the all-reduce operand) | lv (M,B) f64 (dense pass) |
+//              partial (G,S,K) f64 | drift (M,2) f64 + decision | survivor lists: csr_ptr / csr_cnt (M,B) u32,
+//              pool_k u8 + pool_e f64 (64 entries per table row on average)
 //
-// Sinkhorn formulation.  The reference materialises Q = exp(-d~/eps) as (M,K,B) fp64 and divides
-// it in place 4x per iteration.  Here Q_t = exp(a + lu[k] + lv[b]) with a = -d~/eps is never
-// stored: one pass over the fp32 table per iteration evaluates each element once, finishes the
-// column normalisation of iteration t inside a warp (a table row is one column of Q) and
-// accumulates the row sums that iteration t+1 needs.  Per iteration: 4 B/element of HBM traffic
-// instead of the reference's ~80 B/element, and ONE exp per element.
+// Sinkhorn formulation.  The reference materialises Q = exp(-d~/eps) as (M,K,B) fp64 and divides it in place
+// 4x per iteration.  Here Q_t[k,b] = 2^(a + lu[k] + lv[b]), a = -d~ * log2(e)/eps, is never stored.
+//   dense pass   (any K): one pass over the fp32 table per iteration evaluates each element once, finishes the
+//                column normalisation of iteration t inside a warp (a table row is one column of Q) and
+//                accumulates the row sums that iteration t+1 needs: 4 B/element of HBM traffic instead of the
+//                reference's ~80 B/element, and ONE exp2 per element.
+//   sparse passes (K = 256, default): only the elements within 2^-72 of their column's maximum can change an
+//                fp64 sum.  A selection pass finds them (fp32 filter, ballot compaction), evaluates them in
+//                fp64 and emits them as per-row lists; list passes then iterate on the lists alone -- one
+//                multiplication per survivor -- until lu has drifted by more than the selection slack.
+//   Kernels: dist_table / nn_assign, sinkhorn_pass<BEGIN|STEP|FINISH> (dense), sinkhorn_step_sparse (selection),
+//            sinkhorn_step_csr (list), sinkhorn_update (row scaling, drift, U, decision), sinkhorn_reduce,
+//            sinkhorn_expand (Q for API parity).
 #include <math.h>
 #include <stdlib.h>
 

@@ -17,28 +17,6 @@
 
 namespace rc {
 
-__device__ __forceinline__ double exp2_fast(double w) {
-    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-    const double t = w + MAGIC;
-    int n = __double2loint(t);
-    const double f = w - (t - MAGIC);
-    double p = 4.4558179083360645e-10;
-    p = fma(p, f, 7.074194297288521e-09);
-    p = fma(p, f, 1.0178057087733941e-07);
-    p = fma(p, f, 1.3215432535912375e-06);
-    p = fma(p, f, 1.5252733841556773e-05);
-    p = fma(p, f, 0.00015403530463724353);
-    p = fma(p, f, 0.001333355814640647);
-    p = fma(p, f, 0.009618129107587256);
-    p = fma(p, f, 0.055504108664821625);
-    p = fma(p, f, 0.24022650695910158);
-    p = fma(p, f, 0.6931471805599453);
-    p = fma(p, f, 1.0);
-    n = max(n, -1022);
-    n = min(n, 1023);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-
 // N evaluations with the Horner recurrences interleaved coefficient by coefficient (N independent
 // dependency chains in flight: the fp64 pipe has ~16 cycles of latency and this kernel runs 4 warps per
 // scheduler).  CLAMP_HI = false when the caller guarantees w < 1024 (inside the iteration Q <= 1).
