@@ -112,6 +112,16 @@ int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int
  * sinkhorn_algorithm returns (modeling_repconc.py:164-165); call instead of rc_sinkhorn_finish */
 int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, double* Q, int32_t* flags, void* stream);
+/* Single-rank solve = rc_sinkhorn_begin + (iters-1) x rc_sinkhorn_step + rc_sinkhorn_finish with
+ * B_global == B, in one call and bit-identical to that sequence (the row-sum reduction and the row
+ * normalisation fuse into one kernel per iteration because no all-reduce separates them).  This is
+ * what RepCONC.quantize runs when torch.distributed is not initialised (modeling_repconc.py:61). */
+int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
+                      void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, void* stream);
+/* diagnostics of the survivor lists the sparse pass currently holds (K == 256 only): out[0] = entries,
+ * out[1] = longest row, out[2] = rows, out[3 + i] = rows with i*8 <= count < i*8+8 (i < 33). `out` is a
+ * DEVICE array of 36 int64. */
+int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream);
 /* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0 */
 int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,

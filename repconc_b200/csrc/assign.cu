@@ -303,16 +303,22 @@ struct SkState {
     double* drift;    // (M,2)   {max_k, max_k - min_k} of lu - lu_build      (sparse pass)
     double* lu_build; // (M,K)   lu at the last survivor selection             (sparse pass)
     unsigned long long* cursor;  // pool allocation cursor
-    uint32_t* csr_ptr;   // (M,B) first pool entry of a row
-    uint32_t* csr_cnt;   // (M,B) number of survivors of a row
-    uint8_t* pool_k;     // (pool) survivor column
-    double* pool_e;      // (pool) its value 2^(w - rowmax) at selection time
+    uint2* csr;          // (M,B) {pool record of the row in 16-byte units, number of survivors (0: did not fit)}
+    unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
-    uint64_t pool_cap;
+    uint64_t pool_cap;   // pool size in 16-byte units
 };
 
-constexpr unsigned int SK_POOL_CHUNK = 1024;  // pool entries a warp grabs per atomic (>= 256 = one full row)
-constexpr int SK_POOL_PER_ROW = 64;  // survivor pool sized for this many entries per table row on average
+// Survivor record of one table row (pool, 16-byte units).  Lane l of the warp that owns the row looks after the
+// 8 columns k(l,j) = (j>>2)*128 + 4*l + (j&3), j < 8 (the two float4 it loads from the row), and the record is
+//   [0,64)    32 x u16, one per lane: low byte = keep mask over j, high byte = survivors in the lanes below
+//   [64,..)   E = 2^(w - rowmax) of the survivors in (lane, j) order, padded to an even count
+// so a lane of the list pass finds its own survivors contiguous, with their columns implied by the mask:
+// no column index is stored, no per-column table is gathered and the row sums stay in registers.
+constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per atomic (16 KB; a full row is 132)
+constexpr int SK_POOL_PER_ROW = 80;  // survivor pool sized for this many entries per table row on average
+__host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
+__device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
 
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
     size_t off = 0;
@@ -336,24 +342,20 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
     const size_t o_lub = take((size_t)M * K * 8);
     const size_t o_cur = take(256);
     // every warp of the selection pass may strand up to one chunk
-    uint64_t pool = (uint64_t)M * (uint64_t)B * SK_POOL_PER_ROW +
+    uint64_t pool = (uint64_t)M * (uint64_t)B * sk_record_units(SK_POOL_PER_ROW) +
                     (uint64_t)num_sms() * SK_MAX_CTAS_PER_SM * SK_WARPS * SK_POOL_CHUNK;
-    if (pool > 0xFFFFFF00ull) pool = 0xFFFFFF00ull;      // csr_ptr is 32-bit
+    if (pool > 0xFFFFFF00ull) pool = 0xFFFFFF00ull;      // record offsets are 32-bit
     const bool csr = (K == 256);
-    const size_t o_ptr = take(csr ? (size_t)M * B * 4 : 0);
-    const size_t o_cnt = take(csr ? (size_t)M * B * 4 : 0);
+    const size_t o_csr = take(csr ? (size_t)M * B * 8 : 0);
     const size_t o_U = take((size_t)M * K * 8);
-    const size_t o_pk = take(csr ? (size_t)pool : 0);
-    const size_t o_pd = take(csr ? (size_t)pool * 8 : 0);
+    const size_t o_pool = take(csr ? (size_t)pool * 16 : 0);
     if (s) {
         s->drift = (double*)(b + o_drift);
         s->lu_build = (double*)(b + o_lub);
         s->cursor = (unsigned long long*)(b + o_cur);
-        s->csr_ptr = (uint32_t*)(b + o_ptr);
-        s->csr_cnt = (uint32_t*)(b + o_cnt);
+        s->csr = (uint2*)(b + o_csr);
         s->U = (double*)(b + o_U);
-        s->pool_k = (uint8_t*)(b + o_pk);
-        s->pool_e = (double*)(b + o_pd);
+        s->pool = (unsigned char*)(b + o_pool);
         s->pool_cap = pool;
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
@@ -710,14 +712,30 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
             const float cutf = mx - sel_margin;
             // 2. compaction by ballot
             int base = 0;
+            uint32_t keep_mask = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const bool keep = wf[j] >= cutf;
                 const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) my_kl[base + __popc(bal & lt_mask)] = (uint8_t)((j >> 2) * 128 + 4 * lane + (j & 3));
+                if (keep) {
+                    my_kl[base + __popc(bal & lt_mask)] = (uint8_t)sp_col(lane, j);
+                    keep_mask |= 1u << j;
+                }
                 base += __popc(bal);
             }
             const int total = base;
+            // record header of this lane: survivors in the lanes below (exclusive scan) and the keep mask
+            uint32_t meta16;
+            {
+                const int c = __popc(keep_mask);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                meta16 = ((uint32_t)(incl - c) << 8) | keep_mask;
+            }
             __syncwarp();
             // 3. fp64 evaluation of the survivors, shifted by the row maximum
             const double shift = (double)mx;
@@ -743,7 +761,8 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
             //     chunks (one atomic per ~50 rows); the order of rows in the pool is irrelevant, the order inside
             //     a row is the ballot order -> deterministic sums
             {
-                if ((unsigned int)total > chunk_left) {
+                const unsigned int units = sk_record_units((uint32_t)total);
+                if (units > chunk_left) {
                     unsigned long long nb = 0;
                     if (lane == 0) nb = atomicAdd(st.cursor, (unsigned long long)SK_POOL_CHUNK);
                     chunk_base = __shfl_sync(0xffffffffu, nb, 0);
@@ -751,22 +770,29 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
                 }
                 const unsigned long long off = chunk_base;
                 const int64_t row_id = (int64_t)m * B + b_first + (int64_t)r * SK_WARPS;
-                const bool fits = off + (unsigned long long)total <= st.pool_cap;
+                const bool fits = off + (unsigned long long)units <= st.pool_cap;
+                unsigned char* rec = st.pool + (fits ? off : 0ull) * 16ull;
+                double* pe = reinterpret_cast<double*>(rec + 64);
                 if (fits) {
-                    if (lane < total) { st.pool_k[off + lane] = (uint8_t)k0; st.pool_e[off + lane] = q0; }
-                    for (int idx = 32 + lane; idx < total; idx += 32) {
-                        st.pool_k[off + idx] = my_kl[idx];
-                        st.pool_e[off + idx] = my_q[idx];
-                    }
+                    reinterpret_cast<uint16_t*>(rec)[lane] = (uint16_t)meta16;
+                    if (lane == 0 && (total & 1)) pe[total] = 0.0;     // padding entry (copied, never used)
                 } else {
                     bad |= RC_FLAG_SPARSE_UNSAFE;   // pool exhausted: the host re-runs densely
                 }
-                if (lane == 0) {
-                    st.csr_ptr[row_id] = (uint32_t)off;
-                    st.csr_cnt[row_id] = fits ? (uint32_t)total : 0u;
+                // survivor idx of the ballot order -> its place in (lane, j) order: the owner lane's header
+                // gives the lane's first entry, the mask bits below j the place inside the lane
+                for (int bs = 0; bs < total; bs += 32) {
+                    const int idx = bs + lane;
+                    const bool valid = idx < total;
+                    const int k = bs == 0 ? k0 : (valid ? (int)my_kl[idx] : 0);
+                    const double q = bs == 0 ? q0 : (valid ? my_q[idx] : 0.0);
+                    const int j = ((k >> 7) << 2) | (k & 3);
+                    const uint32_t hm = __shfl_sync(0xffffffffu, meta16, (k >> 2) & 31);
+                    if (valid && fits) pe[(hm >> 8) + __popc(hm & ((1u << j) - 1u))] = q;
                 }
-                chunk_base += (unsigned long long)total;
-                chunk_left -= (unsigned int)total;
+                if (lane == 0) st.csr[row_id] = make_uint2((uint32_t)off, fits ? (uint32_t)total : 0u);
+                chunk_base += (unsigned long long)units;
+                chunk_left -= units;
             }
             s = warp_sum(s);
             if (!(s >= 0.5) || !isfinite(s)) bad |= RC_FLAG_NONFINITE;   // the maximum itself contributes ~1
@@ -803,120 +829,199 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
 }
 
 // Iteration on the survivor lists alone (see the comment above sinkhorn_step_sparse_kernel).
-// A list entry carries E = 2^(w - rowmax) as evaluated (fp64) by the selection pass; since then only lu
-// moved, so the element's current value is E * 2^(lu[k] - lu_build[k]) -- up to a per-row constant that
-// the column normalisation removes.  U[k] = 2^(dlu[k] - max_k dlu) is evaluated once per iteration by
-// sinkhorn_update_kernel (256 values per sub-vector), which leaves ONE multiplication per entry here.
-// Granularity: a row has ~40 survivors, so a QUARTER-warp (8 lanes) owns a row and a warp works on four
-// rows at once -- the per-row bookkeeping (offsets, the 3-step shuffle reduction, the reciprocal) is then
-// shared by four rows per instruction.  Each quarter-warp has its own private row-sum array (4 rows of a
-// warp may hit the same column), 32 arrays per CTA, summed in fixed order at the end.
-constexpr int CSR_CTAS_PER_SM = 3;
-constexpr int CSR_PER_LANE = 16;   // entries a lane holds in registers (8 lanes x 16 = 128 per row)
-constexpr int CSR_SMEM = SK_WARPS * 4 * SP_K * 8 + SP_K * 8;   // 64 KB of row sums + U
+// A record carries E = 2^(w - rowmax) as evaluated (fp64) by the selection pass; since then only lu moved, so
+// the element's current value is E * 2^(lu[k] - lu_build[k]) -- up to a per-row constant that the column
+// normalisation removes.  U[k] = 2^(dlu[k] - max_k dlu) is evaluated once per iteration by
+// sinkhorn_update_kernel (256 values per sub-vector).
+// A warp owns a table row; lane l owns the 8 columns k(l,j) of the record layout, so its factors U[k(l,j)]
+// and its 8 row-sum accumulators live in REGISTERS for a whole sub-vector segment: per survivor the pass
+// issues one shared-memory load (the staged E) and two DFMAs -- no column gather, no read-modify-write of a
+// shared row-sum array (the kernel this replaces did three random 8-byte shared accesses per survivor and
+// sat at 78 % of the LSU wavefront limit, half of the wavefronts bank conflicts; profiles/r01_sinkhorn_list_*).
+// Records come in through a per-warp ring of cp.async.bulk copies (one per row, two rows per slot, LP_DEPTH
+// slots in flight, an mbarrier per slot).  Two rows are processed together so that the cross-lane reduction
+// (a transposing butterfly: 5 exchanges for both rows) and the reciprocal are shared.  The row sums are
+// accumulated as sum_b E * rz_b and multiplied by U[k] once per segment.  Every sum has a fixed order.
+constexpr int LP_CTAS_PER_SM = 2;
+constexpr int LP_DEPTH = 4;                                         // slots (row pairs) in flight per warp
+constexpr int LP_SLOT = 2048;                                       // bytes; a pair that does not fit is read from global
+constexpr int LP_OFF_RED = SK_WARPS * LP_DEPTH * LP_SLOT;           // ring: 64 KB
+constexpr int LP_OFF_META = LP_OFF_RED + SK_WARPS * SP_K * 8;       // red : 16 KB
+constexpr int LP_OFF_BAR = LP_OFF_META + SK_WARPS * LP_DEPTH * 16;  // {ptr0, ptr1, cnt0, cnt1} per slot
+constexpr int LP_SMEM = LP_OFF_BAR + SK_WARPS * LP_DEPTH * 8;
 
-__global__ void __launch_bounds__(SK_THREADS, CSR_CTAS_PER_SM)
-sinkhorn_step_csr_kernel(int64_t B, double rBg, int M, SkPart part, const double* __restrict__ drift, int force,
-                         SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char csr_smem[];
-    double* acc_all = reinterpret_cast<double*>(csr_smem);                 // [32 quarter-warps][256]
-    double* U_s = acc_all + SK_WARPS * 4 * SP_K;
+__device__ __forceinline__ uint32_t lp_record_bytes(uint32_t cnt) { return cnt ? 64u + 8u * ((cnt + 1u) & ~1u) : 0u; }
+
+// this lane's survivors of one row: e[j] = E of column k(lane,j) or 0; returns sum_j e[j] * U[j]
+__device__ __forceinline__ double lp_gather_row(const unsigned char* rec, uint32_t hm, const double (&U)[8],
+                                                double (&e)[8]) {
+    const double* p = reinterpret_cast<const double*>(rec + 64) + (hm >> 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        e[j] = 0.0;
+        if ((hm >> j) & 1u) e[j] = *p++;
+    }
+    double sa = e[0] * U[0], sb = e[1] * U[1];
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        sa = fma(e[j], U[j], sa);
+        sb = fma(e[j + 1], U[j + 1], sb);
+    }
+    return sa + sb;
+}
+
+__global__ void __launch_bounds__(SK_THREADS, LP_CTAS_PER_SM)
+sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const double* __restrict__ drift, int force,
+                          SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char lp_smem[];
     if (csr_reselect(drift, M, force)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane >> 3, l8 = lane & 7;                               // quarter-warp, lane inside it
-    double* my_acc = acc_all + (warp * 4 + sub) * SP_K;
+    unsigned char* my_ring = lp_smem + warp * LP_DEPTH * LP_SLOT;
+    double* red_all = reinterpret_cast<double*>(lp_smem + LP_OFF_RED);
+    uint4* my_meta = reinterpret_cast<uint4*>(lp_smem + LP_OFF_META) + warp * LP_DEPTH;
+    const uint32_t my_bars = smem_u32(lp_smem + LP_OFF_BAR) + warp * LP_DEPTH * 8;
     const int g = blockIdx.x;
     const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
     if (t_lo >= t_hi) return;
     const int m_first = (int)(t_lo / part.tpm);
     int bad = 0;
+    uint32_t seq = 0, iss = 0;   // row pairs consumed / issued by this warp since kernel start
+    if (lane == 0)
+        for (int d = 0; d < LP_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
+    fence_barrier_init();
+    __syncwarp();
 
     int64_t t = t_lo;
     while (t < t_hi) {
         const int m = (int)(t / part.tpm);
         const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
-        // rows [b_lo, b_hi) of sub-vector m belong to this CTA; quarter-warp q = warp*4+sub takes b_lo+q, +32, ...
-        const int64_t b_lo = (t - (int64_t)m * part.tpm) * SK_WARPS;
-        const int64_t b_hi = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
-        U_s[threadIdx.x] = st.U[(int64_t)m * SP_K + threadIdx.x];
-        for (int i = l8; i < SP_K; i += 8) my_acc[i] = 0.0;
-        __syncthreads();
-        const int64_t rbase = (int64_t)m * B;
-        // Row meta is fetched one iteration ahead; a lane's first CSR_PER_LANE entries (128 per row) are all
-        // loaded up front into registers -- ONE memory latency per iteration -- and reused for the row-sum
-        // update.  Rows with more survivors than that finish in a (rare) tail loop.
-        // Row order: warp w takes the rows the SAME warp of the selection pass took (b_lo + w, + 8, + 16, ...),
-        // four consecutive ones per iteration (one per quarter-warp).  The selection pass wrote exactly that
-        // sequence back to back into its pool chunk, so every warp here streams a contiguous region of HBM.
-        uint32_t ptr_n = 0;
-        int cnt_n = 0;
-        {
-            const int64_t b = b_lo + warp + (int64_t)SK_WARPS * sub;
-            if (b < b_hi) { ptr_n = st.csr_ptr[rbase + b]; cnt_n = (int)st.csr_cnt[rbase + b]; }
+        // rows of this warp inside the segment: b = b_first + SK_WARPS * i, i < nrows (the rows warp `warp` of
+        // some selection CTA wrote back to back into its pool chunk)
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
+        const int npairs = (nrows + 1) >> 1;
+        const uint2* dir = st.csr + (int64_t)m * B + b_first;
+        double U[8], A[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            U[j] = st.U[(int64_t)m * SP_K + sp_col(lane, j)];
+            A[j] = 0.0;
         }
-        for (int64_t b0 = b_lo + warp; b0 < b_hi; b0 += 4 * SK_WARPS) {   // warp-uniform trip count
-            const bool live = b0 + (int64_t)SK_WARPS * sub < b_hi;
-            const uint32_t ptr = ptr_n;
-            const int total = cnt_n;
-            {
-                const int64_t bn = b0 + (int64_t)SK_WARPS * (4 + sub);
-                const bool ln = bn < b_hi;
-                ptr_n = ln ? st.csr_ptr[rbase + bn] : 0u;
-                cnt_n = ln ? (int)st.csr_cnt[rbase + bn] : 0;
+        // lanes 0 and 1 hold the directory entries of the two rows of the next pair to issue, one pair ahead
+        uint2 dn = make_uint2(0u, 0u);
+        auto fetch_meta = [&](int pair) {
+            const int row = 2 * pair + lane;
+            dn = (lane < 2 && row < nrows) ? dir[(int64_t)row * SK_WARPS] : make_uint2(0u, 0u);
+        };
+        // (no proxy fence before a refill: the slot was only READ through the generic proxy, and those loads have
+        //  delivered their values to the arithmetic before the __syncwarp that precedes the refill)
+        auto issue = [&](int pair) {
+            const uint32_t slot = iss % LP_DEPTH;
+            const uint32_t ptr1 = __shfl_sync(0xffffffffu, dn.x, 1), cnt1 = __shfl_sync(0xffffffffu, dn.y, 1);
+            if (lane == 0) {
+                const uint32_t ptr0 = dn.x, cnt0 = dn.y;
+                const uint32_t len0 = lp_record_bytes(cnt0), len1 = lp_record_bytes(cnt1);
+                const uint32_t bar = my_bars + 8 * slot, dst = smem_u32(my_ring + slot * LP_SLOT);
+                my_meta[slot] = make_uint4(ptr0, ptr1, cnt0, cnt1);
+                const bool staged = len0 + len1 <= (uint32_t)LP_SLOT;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                             "r"(staged ? len0 + len1 : 0u)
+                             : "memory");
+                if (staged && len0)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                        "l"(st.pool + (size_t)ptr0 * 16), "r"(len0), "r"(bar)
+                        : "memory");
+                if (staged && len1)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + len0),
+                        "l"(st.pool + (size_t)ptr1 * 16), "r"(len1), "r"(bar)
+                        : "memory");
             }
-            const uint8_t* pk = st.pool_k + ptr;
-            const double* pe = st.pool_e + ptr;
-            int kk[CSR_PER_LANE];
-            double qq[CSR_PER_LANE];
+            fetch_meta(pair + 1);
+            ++iss;
+        };
+        fetch_meta(0);
+        for (int q = 0; q < npairs && q < LP_DEPTH; ++q) issue(q);
+        __syncwarp();
+
+        for (int q = 0; q < npairs; ++q) {
+            const uint32_t slot = seq % LP_DEPTH;
+            mbar_wait(my_bars + 8 * slot, (seq / LP_DEPTH) & 1u);
+            const uint4 mt = my_meta[slot];                     // {ptr0, ptr1, cnt0, cnt1}
+            const uint32_t len0 = lp_record_bytes(mt.z), len1 = lp_record_bytes(mt.w);
+            uint32_t hm0 = 0u, hm1 = 0u;
+            double e0[8], e1[8], s0, s1;
+            if (len0 + len1 <= (uint32_t)LP_SLOT) {             // (two code paths: shared / global address space)
+                const unsigned char* rec0 = my_ring + slot * LP_SLOT;
+                const unsigned char* rec1 = rec0 + len0;
+                if (mt.z) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+                if (mt.w) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+                s0 = lp_gather_row(rec0, hm0, U, e0);
+                s1 = lp_gather_row(rec1, hm1, U, e1);
+            } else {                                            // oversized pair (rare): straight from the pool
+                const unsigned char* rec0 = st.pool + (size_t)mt.x * 16;
+                const unsigned char* rec1 = st.pool + (size_t)mt.y * 16;
+                if (mt.z) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+                if (mt.w) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+                s0 = lp_gather_row(rec0, hm0, U, e0);
+                s1 = lp_gather_row(rec1, hm1, U, e1);
+            }
+            // both records are in registers: refill the slot LP_DEPTH pairs ahead before the reduction
+            __syncwarp();
+            if (q + LP_DEPTH < npairs) issue(q + LP_DEPTH);
+            // column sums of both rows: lanes 0-15 end up with row 0's, lanes 16-31 with row 1's
+            const bool hi = lane & 16;
+            double a = hi ? s1 : s0;
+            a += __shfl_xor_sync(0xffffffffu, hi ? s0 : s1, 16);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            const bool live = (hi ? mt.w : mt.z) != 0u;
+            if (live && (!(a > 0.0) || !isfinite(a))) bad |= RC_FLAG_NONFINITE;
+            const double rz = live ? __drcp_rn(a) * rBg : 0.0;      // Q / (B_global * column sum)  (:162-163)
+            const double rz0 = __shfl_sync(0xffffffffu, rz, 0), rz1 = __shfl_sync(0xffffffffu, rz, 16);
 #pragma unroll
-            for (int i = 0; i < CSR_PER_LANE; ++i) {
-                const int idx = l8 + 8 * i;
-                const bool v = idx < total;
-                kk[i] = v ? (int)pk[idx] : 0;
-                qq[i] = v ? pe[idx] : 0.0;
+            for (int j = 0; j < 8; ++j) {
+                A[j] = fma(e0[j], rz0, A[j]);
+                A[j] = fma(e1[j], rz1, A[j]);
             }
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < CSR_PER_LANE; ++i) {
-                qq[i] *= U_s[kk[i]];
-                s += qq[i];
-            }
-            for (int idx = 8 * CSR_PER_LANE + l8; idx < total; idx += 8) s = fma(pe[idx], U_s[pk[idx]], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (live && (!(s > 0.0) || !isfinite(s))) bad |= RC_FLAG_NONFINITE;
-            const double rz = __drcp_rn(s) * rBg;
-#pragma unroll
-            for (int i = 0; i < CSR_PER_LANE; ++i)
-                if (l8 + 8 * i < total) my_acc[kk[i]] = fma(qq[i], rz, my_acc[kk[i]]);
-            for (int idx = 8 * CSR_PER_LANE + l8; idx < total; idx += 8) {
-                const int k = pk[idx];
-                my_acc[k] = fma(pe[idx] * U_s[k], rz, my_acc[k]);
-            }
+            ++seq;
         }
-        __syncthreads();
+        // row sums of the segment: warp 0..7 in order (deterministic)
         {
+            double* my_red = red_all + warp * SP_K;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) my_red[sp_col(lane, j)] = U[j] * A[j];
+            __syncthreads();
             double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * SP_K;
-            double sum = acc_all[threadIdx.x];
-#pragma unroll 8
-            for (int w = 1; w < SK_WARPS * 4; ++w) sum += acc_all[w * SP_K + threadIdx.x];
+            double sum = red_all[threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < SK_WARPS; ++w) sum += red_all[w * SP_K + threadIdx.x];
             dst[threadIdx.x] = sum;
+            __syncthreads();
         }
-        __syncthreads();
         t = t_end;
     }
     if (bad) atomicOr(flags, bad);
 }
 
-// P[m,k] = sum over the CTAs that touched sub-vector m, in CTA order (deterministic).
-__global__ void __launch_bounds__(256)
-sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, double* __restrict__ P,
-                       int csr_mode, int M, int force, SkState st) {
+// P[m,k] = sum over the CTAs that touched sub-vector m, in CTA order (deterministic).  One block per m.
+// The rows of `partial` that hold sub-vector m are located once per block (they belong to a contiguous range of
+// CTAs), then every thread sums its columns over that list with independent loads.
+constexpr int SK_RED_LIST = 256;
+__device__ __forceinline__ void sk_reduce_block(const double* __restrict__ partial, const SkPart& part_in,
+                                                const SkPart& part_list, int K, double* __restrict__ P, int csr_mode,
+                                                int M, int force, const SkState& st, int* s_off) {
     const int m = blockIdx.x;
+    // the partials were written by the pass that did the work: the list pass has its own grid
+    const bool resel = csr_mode && csr_reselect(st.drift, M, force);
+    const SkPart part = (csr_mode && !resel) ? part_list : part_in;
     if (csr_mode) {
         // the pass that just ran re-selected the survivors iff csr_reselect() says so: remember its lu
-        if (csr_reselect(st.drift, M, force))
+        if (resel)
             for (int k = threadIdx.x; k < K; k += blockDim.x) st.lu_build[(int64_t)m * K + k] = st.lu[(int64_t)m * K + k];
         if (m == 0 && threadIdx.x == 0) *st.cursor = 0ull;   // only live during a selection pass
     }
@@ -926,29 +1031,53 @@ sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part, int K, d
     int g_last = (int)((m_hi * part.G) / part.total) + 1;
     if (g_first < 0) g_first = 0;
     if (g_last > part.G - 1) g_last = part.G - 1;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        double sum = 0.0;
-        for (int g = g_first; g <= g_last; ++g) {
+    double sum[2] = {0.0, 0.0};                              // K <= 512, blockDim == 256: two columns per thread
+    for (int g0 = g_first; g0 <= g_last; g0 += SK_RED_LIST) {
+        const int n = min(SK_RED_LIST, g_last - g0 + 1);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int g = g0 + i;
             const int64_t lo = sk_lo(part, g), hi = sk_lo(part, g + 1);
-            if (lo >= hi || hi <= m_lo || lo >= m_hi) continue;
-            const int slot = m - (int)(lo / part.tpm);
-            sum += partial[((int64_t)g * part.S + slot) * K + k];
+            const bool hit = lo < hi && hi > m_lo && lo < m_hi;
+            s_off[i] = hit ? g * part.S + (m - (int)(lo / part.tpm)) : -1;
         }
-        P[(int64_t)m * K + k] = sum;
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int k = threadIdx.x + c * 256;
+            if (k < K) {
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const int o = s_off[i];
+                    if (o >= 0) sum[c] += partial[(int64_t)o * K + k];
+                }
+            }
+        }
     }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int k = threadIdx.x + c * 256;
+        if (k < K) P[(int64_t)m * K + k] = sum[c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part_in, SkPart part_list, int K,
+                       double* __restrict__ P, int csr_mode, int M, int force, SkState st) {
+    __shared__ int s_off[SK_RED_LIST];
+    sk_reduce_block(partial, part_in, part_list, K, P, csr_mode, M, force, st, s_off);
 }
 
 // row normalisation in log2 form: lu[m,k] -= log2(K * P[m,k])     (Q /= sum_of_rows; Q /= K, :158-159)
 // Also tracks, per sub-vector, how far lu has moved since the last survivor selection
 // (drift[m] = {max_k, max_k - min_k} of lu - lu_build), which is what decides between the list pass and a
 // new selection, and checks that every centroid kept a sane share of the mass through the last column
-// normalisation (the premise of the sparse pass's row-sum bound).
-__global__ void __launch_bounds__(256)
-sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, const double* __restrict__ lu_build,
-                       int K, double Kd, int check_mass, double* __restrict__ drift, double* __restrict__ U,
-                       int32_t* __restrict__ flags) {
-    __shared__ double red_mx[8], red_mn[8];
-    __shared__ double s_dmax;
+// normalisation (the premise of the sparse pass's row-sum bound).  One block per m.
+__device__ __forceinline__ void sk_update_block(double* __restrict__ lu, const double* __restrict__ P,
+                                                const double* __restrict__ lu_build, int K, double Kd,
+                                                int check_mass, double* __restrict__ drift, double* __restrict__ U,
+                                                int32_t* __restrict__ flags, double* red_mx, double* red_mn,
+                                                double* s_dmax) {
     const int m = blockIdx.x;
     double dmax = -INFINITY, dmin = INFINITY;
     int bad = 0;
@@ -978,8 +1107,9 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, co
         }
         drift[2 * m] = dmax;
         drift[2 * m + 1] = dmax - dmin;
-        s_dmax = dmax;
+        *s_dmax = dmax;
         // last block to finish publishes the iteration's decision: re-select iff any spread exceeds the slack
+        // (every block has read the previous decision before it gets here)
         int* ctl = reinterpret_cast<int*>(drift + 2 * gridDim.x);
         __threadfence();
         if (atomicAdd(ctl + 1, 1) == (int)gridDim.x - 1) {
@@ -995,12 +1125,35 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, co
     }
     __syncthreads();
     // per-column factor of the list pass: 2^(dlu - max dlu) in (0, 1]
-    const double dm = s_dmax;
+    const double dm = *s_dmax;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const int64_t i = (int64_t)m * K + k;
         U[i] = exp2(lu[i] - lu_build[i] - dm);
     }
     if (bad) atomicOr(flags, bad);
+}
+
+__global__ void __launch_bounds__(256)
+sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, const double* __restrict__ lu_build,
+                       int K, double Kd, int check_mass, double* __restrict__ drift, double* __restrict__ U,
+                       int32_t* __restrict__ flags) {
+    __shared__ double red_mx[8], red_mn[8];
+    __shared__ double s_dmax;
+    sk_update_block(lu, P, lu_build, K, Kd, check_mass, drift, U, flags, red_mx, red_mn, &s_dmax);
+}
+
+// reduce + update in one launch: the single-rank solve (rc_sinkhorn_solve) has no all-reduce between them.
+// Same arithmetic, same order as the two kernels above.
+__global__ void __launch_bounds__(256)
+sinkhorn_reduce_update_kernel(const double* __restrict__ partial, SkPart part_in, SkPart part_list, int K, int csr_mode,
+                              int M, int force, int check_mass, SkState st, int32_t* __restrict__ flags) {
+    __shared__ int s_off[SK_RED_LIST];
+    __shared__ double red_mx[8], red_mn[8];
+    __shared__ double s_dmax;
+    sk_reduce_block(partial, part_in, part_list, K, st.P, csr_mode, M, force, st, s_off);
+    __syncthreads();   // P[m,:] and lu_build[m,:] of this block are final (each element is re-read by its writer)
+    sk_update_block(st.lu, st.P, st.lu_build, K, (double)K, check_mass, st.drift, st.U, flags, red_mx, red_mn,
+                    &s_dmax);
 }
 
 // Transport plan Q (M,K,B) fp64 from the row scaling alone (API parity with sinkhorn_algorithm's return
@@ -1024,6 +1177,16 @@ sinkhorn_expand_kernel(const float* __restrict__ table, int64_t B, int M, int K,
     s = warp_sum(s);
     for (int k = lane; k < K; k += 32)
         Q[((int64_t)m * K + k) * B + b] = exp2(fma(-(double)row[k], scale2, lu[k]) - mx) / s;
+}
+
+__global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t rows, unsigned long long* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const unsigned int c = csr[i].y;
+    atomicAdd(out + 0, (unsigned long long)c);
+    atomicMax(out + 1, (unsigned long long)c);
+    atomicAdd(out + 2, 1ull);
+    atomicAdd(out + 3 + min(c >> 3, 32u), 1ull);
 }
 
 __global__ void fill_f64_kernel(double* p, int64_t n, double v) {
@@ -1066,8 +1229,8 @@ static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, 
 }
 
 static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaStream_t st, int csr_mode = 0,
-                         int force = 0) {
-    sinkhorn_reduce_kernel<<<M, 256, 0, st>>>(s.partial, p, K, s.P, csr_mode, M, force, s);
+                         int force = 0, const SkPart* p_list = nullptr) {
+    sinkhorn_reduce_kernel<<<M, 256, 0, st>>>(s.partial, p, p_list ? *p_list : p, K, s.P, csr_mode, M, force, s);
     RC_CHECK_LAUNCH("sinkhorn_reduce_kernel");
     return RC_OK;
 }
@@ -1077,6 +1240,28 @@ static int launch_update(const SkState& s, int M, int K, double Bg, int check_ma
     (void)Bg;
     sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, s.lu_build, K, (double)K, check_mass, s.drift, s.U, flags);
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
+    return RC_OK;
+}
+
+// One sparse iteration (K == 256): the selection pass and the list pass are both launched; exactly one of them
+// works (device-side decision from the drift the update kernel just wrote; force = 1: select).
+static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, int M, double eps, int force,
+                              const SkState& s, int32_t* flags, cudaStream_t st, SkPart* ps_out, SkPart* pl_out) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM));
+        attr_done = true;
+    }
+    const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM), pl = sk_partition(B, M, LP_CTAS_PER_SM);
+    const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
+    sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, rBg, M, scale2, ps, s.lu, s.drift, force, s,
+                                                                  s.partial, flags);
+    RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
+    sinkhorn_step_list_kernel<<<pl.G, SK_THREADS, LP_SMEM, st>>>(B, rBg, M, pl, s.drift, force, s, s.partial, flags);
+    RC_CHECK_LAUNCH("sinkhorn_step_list_kernel");
+    *ps_out = ps;
+    *pl_out = pl;
     return RC_OK;
 }
 
@@ -1161,6 +1346,17 @@ RC_API int rc_dist_table(const float* x, int64_t ldx, const float* centroids, in
     return rc;
 }
 
+static int sk_reset(const SkState& s, int M, int K, cudaStream_t st) {
+    const int64_t n = (int64_t)M * K;
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, n, 0.0);
+    RC_CHECK_LAUNCH("fill_f64_kernel");
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu_build, n, 0.0);
+    RC_CHECK_LAUNCH("fill_f64_kernel");
+    RC_CUDA(cudaMemsetAsync(s.drift + 2 * M, 0, 16, st));
+    RC_CUDA(cudaMemsetAsync(s.cursor, 0, 8, st));
+    return RC_OK;
+}
+
 RC_API size_t rc_sinkhorn_state_bytes(int64_t B, int M, int K) {
     if (B < 1 || M < 1 || K < 1) return 0;
     const SkPart p = sk_partition(B, M);
@@ -1192,16 +1388,60 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    const int64_t n = (int64_t)M * K;
-    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, n, 0.0);
-    RC_CHECK_LAUNCH("fill_f64_kernel");
-    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu_build, n, 0.0);
-    RC_CHECK_LAUNCH("fill_f64_kernel");
-    RC_CUDA(cudaMemsetAsync(s.drift + 2 * M, 0, 16, st));
-    RC_CUDA(cudaMemsetAsync(s.cursor, 0, 8, st));
+    rc = sk_reset(s, M, K, st);
+    if (rc) return rc;
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
     return launch_reduce(p, s, M, K, st);
+}
+
+/* Single-rank solve: rc_sinkhorn_begin + (iters - 1) x rc_sinkhorn_step + rc_sinkhorn_finish in one call.  With no
+ * all-reduce between the row-sum reduction and the row normalisation the two run as ONE kernel per iteration
+ * (sinkhorn_reduce_update_kernel); everything else is the kernels of the step-wise entry points in the same
+ * order, so the results are bit-identical to the step-wise sequence with B_global == B. */
+RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
+                             void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, void* stream) {
+    int rc = sk_args(table, B, M, K, eps, state, flags);
+    if (rc) return rc;
+    RC_REQUIRE(minmax, "rc_sinkhorn_solve: null minmax");
+    RC_REQUIRE(iters >= 0, "rc_sinkhorn_solve: iters < 0");
+    RC_REQUIRE(codes_mb || codes_u8, "rc_sinkhorn_solve: no output");
+    RC_REQUIRE(!codes_u8 || K <= 256, "rc_sinkhorn_solve: uint8 codes need K <= 256");
+    cudaStream_t st = (cudaStream_t)stream;
+    const SkPart p = sk_partition(B, M);
+    SkState s;
+    sk_layout(B, M, K, p, state, &s);
+    rc = sk_reset(s, M, K, st);
+    if (rc) return rc;
+    rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
+    if (rc) return rc;
+    if (iters >= 1 && B == 1) {
+        // one column: every entry is exactly 1/K after the row normalisation (see rc_sinkhorn_finish)
+        if (codes_mb) RC_CUDA(cudaMemsetAsync(codes_mb, 0, (size_t)M * B * sizeof(int64_t), st));
+        if (codes_u8) RC_CUDA(cudaMemsetAsync(codes_u8, 0, (size_t)M * B, st));
+        return RC_OK;
+    }
+    const bool sparse = K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
+    // which pass wrote the partials the next reduce+update consumes
+    int csr_mode = 0, force = 0;
+    SkPart pin = p, plist = p;
+    for (int it = 0; it < iters; ++it) {
+        const bool last = it == iters - 1;
+        sinkhorn_reduce_update_kernel<<<M, 256, 0, st>>>(s.partial, pin, plist, K, csr_mode, M, force,
+                                                         (!last && sparse && it > 0) ? 1 : 0, s, flags);
+        RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
+        if (last) break;
+        if (sparse) {
+            force = it == 0 ? 1 : 0;
+            rc = launch_sparse_step(table, B, B, M, eps, force, s, flags, st, &pin, &plist);
+            if (rc) return rc;
+            csr_mode = 1;
+        } else {
+            rc = launch_pass<SK_STEP>(table, nullptr, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
+            if (rc) return rc;
+        }
+    }
+    return launch_pass<SK_FINISH>(table, nullptr, B, (double)B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
 }
 
 RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
@@ -1220,31 +1460,30 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
     rc = launch_update(s, M, K, (double)B_global, (sparse && step_index > 0) ? 1 : 0, flags, st);
     if (rc) return rc;
     if (sparse) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SP_SMEM));
-            RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         CSR_SMEM));
-            attr_done = true;
-        }
-        // selection pass and list pass are both launched; exactly one of them works (device-side decision
-        // from the drift the update kernel just wrote; the first step always selects)
-        const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM);
         const int force = step_index == 0 ? 1 : 0;
-        const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
-        sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, rBg, M, scale2, ps, s.lu, s.drift,
-                                                                      force, s, s.partial, flags);
-        RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
-        sinkhorn_step_csr_kernel<<<ps.G, SK_THREADS, CSR_SMEM, st>>>(B, rBg, M, ps, s.drift, force, s, s.partial,
-                                                                    flags);
-        RC_CHECK_LAUNCH("sinkhorn_step_csr_kernel");
-        return launch_reduce(ps, s, M, K, st, 1, force);
+        SkPart ps, pl;
+        rc = launch_sparse_step(table, B, B_global, M, eps, force, s, flags, st, &ps, &pl);
+        if (rc) return rc;
+        return launch_reduce(ps, s, M, K, st, 1, force, &pl);
     }
     rc = launch_pass<SK_STEP>(const_cast<float*>(table), nullptr, B, (double)B_global, M, K, eps, p, s, nullptr,
                               nullptr, flags, st);
     if (rc) return rc;
     return launch_reduce(p, s, M, K, st);
+}
+
+RC_API int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream) {
+    RC_REQUIRE(state && out && B >= 1 && M >= 1, "rc_sinkhorn_list_stats: bad argument");
+    RC_REQUIRE(K == SP_K, "rc_sinkhorn_list_stats: survivor lists exist for K == 256 only (K=%d)", K);
+    cudaStream_t st = (cudaStream_t)stream;
+    const SkPart p = sk_partition(B, M);
+    SkState s;
+    sk_layout(B, M, K, p, state, &s);
+    RC_CUDA(cudaMemsetAsync(out, 0, 36 * sizeof(int64_t), st));
+    const int64_t rows = (int64_t)M * B;
+    list_stats_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(s.csr, rows, (unsigned long long*)out);
+    RC_CHECK_LAUNCH("list_stats_kernel");
+    return RC_OK;
 }
 
 RC_API int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,

@@ -130,13 +130,30 @@ class CudaAssignKernels:
         self.tab, self.minmax, self.flags = dist_table(self.x, self.c)
         return self.minmax
 
-    def begin(self, eps):
+    def _alloc_state(self):
         nbytes = self.lib.rc_sinkhorn_state_bytes(self.B, self.M, self.K)
         self.state = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         p = self.lib.rc_sinkhorn_rowsum_ptr(self.state.data_ptr(), self.B, self.M, self.K)
         off = p - self.state.data_ptr()
         self.P = self.state[off: off + self.M * self.K * 8].view(torch.float64).view(self.M, self.K)
         self.nsteps = 0
+
+    def solve(self, eps, iters, uint8=False):
+        """single-rank Sinkhorn + argmax in one library call (rc_sinkhorn_solve); needs table() first"""
+        self._alloc_state()
+        if uint8:
+            out = torch.empty((self.B, self.M), dtype=torch.uint8, device=self.device)
+            mb, u8 = None, out.data_ptr()
+        else:
+            out = torch.empty((self.M, self.B), dtype=torch.int64, device=self.device)
+            mb, u8 = out.data_ptr(), None
+        _lib.check(self.lib.rc_sinkhorn_solve(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, self.M, self.K,
+                                              float(eps), int(iters), self.state.data_ptr(), mb, u8,
+                                              self.flags.data_ptr(), _stream()), "rc_sinkhorn_solve")
+        return out if uint8 else out.t()
+
+    def begin(self, eps):
+        self._alloc_state()
         _lib.check(self.lib.rc_sinkhorn_begin(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, self.M, self.K,
                                               float(eps), self.state.data_ptr(), self.flags.data_ptr(), _stream()),
                    "rc_sinkhorn_begin")
@@ -186,6 +203,9 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
         dist.all_reduce(minmax, dist.ReduceOp.MAX, group=group)
         minmax[1].neg_()
     B_global = kern.B * world
+    if not distributed and hasattr(kern, "solve") and not _stepwise():
+        codes = kern.solve(eps, max(int(iters), 0), uint8=uint8)
+        return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense)
     P = kern.begin(eps)
     # row-sum exchange: one-shot NVLink peer-memory all-reduce when available, NCCL otherwise
     reducer = None
@@ -206,6 +226,16 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
     if distributed and iters >= 1:
         sum_rows(P)
     codes = kern.finish(eps, iters >= 1, uint8=uint8, B_global=B_global)
+    return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense)
+
+
+def _stepwise():
+    """RC_SINKHORN_STEPWISE=1: single-rank assignments also go through begin/step/finish (tests, debugging)"""
+    import os
+    return os.environ.get("RC_SINKHORN_STEPWISE", "0") not in ("", "0")
+
+
+def _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense):
     flags = kern.read_flags()
     if flags & FLAG_SPARSE_UNSAFE and not _retry_dense:
         # the sparse pass's error bound did not hold for this input (a centroid kept < 2^-12/K of mass):

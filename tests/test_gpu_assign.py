@@ -206,3 +206,66 @@ def test_sparse_unsafe_flag_triggers_dense_rerun(oracle):
     c[:, 5, :] += 40.0                              # one outlier centroid per sub-vector
     got = ops.constrained_assign(_dev(x), _dev(c), 0.003, 10, distributed=False).cpu().numpy()
     assert np.array_equal(got, oracle.constrained_assign(x, c, 0.003, 10)["codes"])
+
+
+@pytest.mark.parametrize("shape", [(2048, 48, 16, 20), (300, 96, 8, 7), (1000, 32, 24, 3), (64, 4, 16, 1),
+                                   (64, 4, 16, 0), (1, 4, 16, 5)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_solve_matches_stepwise(shape, dense):
+    """rc_sinkhorn_solve (one call, fused reduce+update) is bit-identical to begin/step/finish:
+    same codes, same row sums P."""
+    from repconc_b200 import ops
+    B, M, ds, T = shape
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((B, M * ds), generator=gen, device="cuda")
+    c = torch.randn((M, 256, ds), generator=gen, device="cuda")
+    ks = ops.CudaAssignKernels(x, c)
+    prev = ks.set_dense(dense)
+    try:
+        ks.table()
+        P = ks.begin(0.003)
+        for _ in range(max(T - 1, 0)):
+            P = ks.step(0.003, B)
+        codes_step = ks.finish(0.003, T >= 1).clone()
+        kf = ops.CudaAssignKernels(x, c)
+        kf.table()
+        codes_solve = kf.solve(0.003, T)
+        assert torch.equal(codes_step, codes_solve)
+        assert ks.read_flags() == kf.read_flags()
+        if T >= 2 and B > 1:
+            assert torch.equal(ks.P, kf.P)
+        u8 = ops.CudaAssignKernels(x, c)
+        u8.table()
+        assert torch.equal(u8.solve(0.003, T, uint8=True).long(), codes_solve)
+    finally:
+        ks.set_dense(prev)
+
+
+def test_list_pass_oversized_rows():
+    """Rows with more survivors than a ring slot holds (near-duplicate centroids make whole rows survive)
+    take the list pass's global-memory path: codes must still match the dense pass and the step-wise API."""
+    from repconc_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    B, M, ds = 777, 6, 16
+    x = torch.randn((B, M * ds), generator=gen, device="cuda")
+    c = torch.randn((M, 1, ds), generator=gen, device="cuda") + 1e-3 * torch.randn((M, 256, ds), generator=gen,
+                                                                                    device="cuda")
+    out = {}
+    for dense in (False, True):
+        k = ops.CudaAssignKernels(x, c)
+        prev = k.set_dense(dense)
+        try:
+            k.table()
+            out[dense] = (k.solve(0.003, 12).clone(), k.P.clone(), k.read_flags())
+            if not dense:
+                st = torch.zeros(36, dtype=torch.int64, device="cuda")
+                from repconc_b200 import _lib
+                _lib.check(k.lib.rc_sinkhorn_list_stats(k.state.data_ptr(), B, M, 256, st.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream), "stats")
+                assert int(st[1]) > 128, st[:3]          # the case really has oversized rows
+        finally:
+            k.set_dense(prev)
+    assert out[False][2] == 0 and out[True][2] == 0
+    assert torch.equal(out[False][0], out[True][0])
+    rel = ((out[False][1] - out[True][1]).abs() / out[True][1]).max().item()
+    assert rel < 1e-12, rel
