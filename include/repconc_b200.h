@@ -153,6 +153,11 @@ int rc_peer_allreduce_f64(const uint64_t* peer_buffers_host, int rank, int W, in
 int rc_decode(const int64_t* codes, int64_t stride_b, int64_t stride_m, const uint8_t* codes_u8,
               const float* centroids, int64_t B, int M, int K, int ds, float* out, int32_t* flags,
               void* stream);
+/* counts[m,k] = #{b : codes[b,m] == k} (int32, (M,K)): the code histogram of eval_balance
+ * (finetune_repconc.py:604-611) and the cluster sizes of the k-means warm-up (run_warmup.py:85-132).
+ * codes as for rc_decode; out-of-range codes set *flags |= 4 and are not counted. */
+int rc_code_histogram(const int64_t* codes, int64_t stride_b, int64_t stride_m, const uint8_t* codes_u8,
+                      int64_t B, int M, int K, int32_t* counts, int32_t* flags, void* stream);
 size_t rc_decode_bwd_workspace_bytes(int64_t B, int M, int K, int ds);
 int rc_decode_bwd(const int64_t* codes, int64_t stride_b, int64_t stride_m, const float* grad_q,
                   int64_t ldg, int64_t B, int M, int K, int ds, float* grad_c, void* workspace,

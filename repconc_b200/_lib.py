@@ -39,6 +39,7 @@ SIGNATURES = {
     "rc_peer_allreduce_buffer_bytes": (c_size, [c_i64]),
     "rc_peer_allreduce_f64": (c_int, [c_ptr, c_int, c_int, c_i64, ctypes.c_uint32, c_ptr, c_ptr, c_ptr]),
     "rc_decode": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "rc_code_histogram": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "rc_decode_bwd_workspace_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
     "rc_decode_bwd": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "rc_mse_workspace_bytes": (c_size, [c_i64, c_int, c_int, c_int]),

@@ -307,6 +307,7 @@ struct SkState {
     unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
     uint64_t pool_cap;   // pool size in 16-byte units
+    double slack;        // selection depth beyond SK_MARGIN (log2 units)
 };
 
 // Survivor record of one table row (pool, 16-byte units).  Lane l of the warp that owns the row looks after the
@@ -319,6 +320,19 @@ constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per 
 constexpr int SK_POOL_PER_ROW = 80;  // survivor pool sized for this many entries per table row on average
 __host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
 __device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
+
+constexpr double SK_SLACK = 24.0;        // default extra selection depth = admissible drift of lu between selections
+// (run-time tunable for experiments: env RC_SINKHORN_SLACK; deeper selection = longer lists, fewer re-selections;
+//  the error bound depends on SK_MARGIN only)
+static double sk_slack() {
+    static double v = -1.0;
+    if (v < 0.0) {
+        const char* e = getenv("RC_SINKHORN_SLACK");
+        v = (e && e[0]) ? atof(e) : SK_SLACK;
+        if (!(v >= 1.0 && v <= 400.0)) v = SK_SLACK;
+    }
+    return v;
+}
 
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
     size_t off = 0;
@@ -356,6 +370,7 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
         s->csr = (uint2*)(b + o_csr);
         s->U = (double*)(b + o_U);
         s->pool = (unsigned char*)(b + o_pool);
+        s->slack = sk_slack();
         s->pool_cap = pool;
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
@@ -617,7 +632,7 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 // after RC_FLAG_SPARSE_UNSAFE.
 // ---------------------------------------------------------------------------------------------
 constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
-constexpr double SK_SLACK = 24.0;        // extra selection depth = admissible drift of lu between selections
+
 
 // true -> this iteration re-selects (and re-emits) the survivors; false -> it iterates on the lists
 // (the decision is made once per iteration by the last block of sinkhorn_update_kernel and published as
@@ -664,7 +679,7 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
     const float scale32 = (float)scale2;
     const uint32_t row_bytes = SP_K * 4u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const float sel_margin = (float)(SK_MARGIN + SK_SLACK) + 0.5f;
+    const float sel_margin = (float)(SK_MARGIN + st.slack) + 0.5f;
     unsigned long long chunk_base = 0;   // this warp's current pool chunk
     unsigned int chunk_left = 0;
 
@@ -1075,9 +1090,9 @@ sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part_in, SkPar
 // normalisation (the premise of the sparse pass's row-sum bound).  One block per m.
 __device__ __forceinline__ void sk_update_block(double* __restrict__ lu, const double* __restrict__ P,
                                                 const double* __restrict__ lu_build, int K, double Kd,
-                                                int check_mass, double* __restrict__ drift, double* __restrict__ U,
-                                                int32_t* __restrict__ flags, double* red_mx, double* red_mn,
-                                                double* s_dmax) {
+                                                int check_mass, double slack, double* __restrict__ drift,
+                                                double* __restrict__ U, int32_t* __restrict__ flags, double* red_mx,
+                                                double* red_mn, double* s_dmax) {
     const int m = blockIdx.x;
     double dmax = -INFINITY, dmin = INFINITY;
     int bad = 0;
@@ -1117,7 +1132,7 @@ __device__ __forceinline__ void sk_update_block(double* __restrict__ lu, const d
             int resel = 0;
             for (int i = 0; i < (int)gridDim.x; ++i) {
                 const double sp = reinterpret_cast<volatile double*>(drift)[2 * i + 1];
-                if (!(sp <= SK_SLACK)) resel = 1;   // also NaN
+                if (!(sp <= slack)) resel = 1;   // also NaN
             }
             ctl[0] = resel;
             ctl[1] = 0;
@@ -1135,11 +1150,11 @@ __device__ __forceinline__ void sk_update_block(double* __restrict__ lu, const d
 
 __global__ void __launch_bounds__(256)
 sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, const double* __restrict__ lu_build,
-                       int K, double Kd, int check_mass, double* __restrict__ drift, double* __restrict__ U,
-                       int32_t* __restrict__ flags) {
+                       int K, double Kd, int check_mass, double slack, double* __restrict__ drift,
+                       double* __restrict__ U, int32_t* __restrict__ flags) {
     __shared__ double red_mx[8], red_mn[8];
     __shared__ double s_dmax;
-    sk_update_block(lu, P, lu_build, K, Kd, check_mass, drift, U, flags, red_mx, red_mn, &s_dmax);
+    sk_update_block(lu, P, lu_build, K, Kd, check_mass, slack, drift, U, flags, red_mx, red_mn, &s_dmax);
 }
 
 // reduce + update in one launch: the single-rank solve (rc_sinkhorn_solve) has no all-reduce between them.
@@ -1152,8 +1167,8 @@ sinkhorn_reduce_update_kernel(const double* __restrict__ partial, SkPart part_in
     __shared__ double s_dmax;
     sk_reduce_block(partial, part_in, part_list, K, st.P, csr_mode, M, force, st, s_off);
     __syncthreads();   // P[m,:] and lu_build[m,:] of this block are final (each element is re-read by its writer)
-    sk_update_block(st.lu, st.P, st.lu_build, K, (double)K, check_mass, st.drift, st.U, flags, red_mx, red_mn,
-                    &s_dmax);
+    sk_update_block(st.lu, st.P, st.lu_build, K, (double)K, check_mass, st.slack, st.drift, st.U, flags, red_mx,
+                    red_mn, &s_dmax);
 }
 
 // Transport plan Q (M,K,B) fp64 from the row scaling alone (API parity with sinkhorn_algorithm's return
@@ -1238,7 +1253,8 @@ static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaSt
 static int launch_update(const SkState& s, int M, int K, double Bg, int check_mass, int32_t* flags,
                          cudaStream_t st) {
     (void)Bg;
-    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, s.lu_build, K, (double)K, check_mass, s.drift, s.U, flags);
+    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, s.lu_build, K, (double)K, check_mass, s.slack, s.drift, s.U,
+                                              flags);
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
 }

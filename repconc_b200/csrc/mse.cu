@@ -273,6 +273,45 @@ RC_API int rc_decode(const int64_t* codes, int64_t stride_b, int64_t stride_m, c
     return RC_OK;
 }
 
+// counts[m,k] = #{b : codes[b,m] == k}: the code histogram of eval_balance (finetune_repconc.py:604-611) and the
+// cluster sizes of the k-means warm-up.  Integer atomics on a shared-memory histogram -> deterministic.
+__global__ void __launch_bounds__(256)
+code_histogram_kernel(const int64_t* __restrict__ codes, int64_t sb, int64_t sm, const uint8_t* __restrict__ codes_u8,
+                      int64_t B, int M, int K, int64_t rows_per_block, int32_t* __restrict__ counts,
+                      int32_t* __restrict__ flags) {
+    extern __shared__ int32_t hist[];
+    const int m = blockIdx.y;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const int64_t b0 = (int64_t)blockIdx.x * rows_per_block, b1 = min(B, b0 + rows_per_block);
+    bool bad = false;
+    for (int64_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
+        const int64_t k = codes_u8 ? (int64_t)codes_u8[b * M + m] : codes[b * sb + (int64_t)m * sm];
+        if (k < 0 || k >= K) bad = true;
+        else atomicAdd(&hist[k], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (hist[k]) atomicAdd(&counts[(int64_t)m * K + k], hist[k]);
+    if (bad) atomicOr(flags, RC_FLAG_BADCODE);
+}
+
+RC_API int rc_code_histogram(const int64_t* codes, int64_t stride_b, int64_t stride_m, const uint8_t* codes_u8,
+                             int64_t B, int M, int K, int32_t* counts, int32_t* flags, void* stream) {
+    RC_REQUIRE((codes != nullptr) != (codes_u8 != nullptr), "rc_code_histogram: pass exactly one of codes / codes_u8");
+    RC_REQUIRE(counts && flags && B >= 0 && M >= 1 && M <= 65535 && K >= 1 && K <= 8192,
+               "rc_code_histogram: bad argument B=%lld M=%d K=%d", (long long)B, M, K);
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * K * sizeof(int32_t), st));
+    if (B == 0) return RC_OK;
+    const int64_t rows_per_block = 4096;
+    dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), (unsigned)M);
+    code_histogram_kernel<<<grid, 256, (size_t)K * sizeof(int32_t), st>>>(codes, stride_b, stride_m, codes_u8, B, M, K,
+                                                                        rows_per_block, counts, flags);
+    RC_CHECK_LAUNCH("code_histogram_kernel");
+    return RC_OK;
+}
+
 RC_API size_t rc_decode_bwd_workspace_bytes(int64_t B, int M, int K, int ds) {
     if (B < 1) return 0;
     return scatter_ws_bytes(B, M, K, ds);

@@ -142,3 +142,27 @@ def test_sum_order_model(oracle):
         want = ON.sum_last_torch_order(v)
         got = np.array([oracle.sum_torch_order(row) for row in v], np.float32)
         assert np.array_equal(want, got), n
+
+
+def test_warmup_oracle_properties(oracle):
+    """oracle/warmup_np.py (k-means PQ + OPQ restatement, parity unpinned w.r.t. Faiss): Lloyd's objective
+    never increases, empty clusters are re-seeded, the Procrustes rotation is orthogonal and optimal."""
+    from oracle import warmup_np as W
+    r = np.random.default_rng(1)
+    centres = r.standard_normal((40, 32)).astype(np.float32)
+    x = (centres[r.integers(0, 40, 4096)] + 0.35 * r.standard_normal((4096, 32))).astype(np.float32)
+    c0 = x[r.permutation(4096)[:16]].reshape(16, 4, 8).transpose(1, 0, 2).copy()
+    c, objs = W.train_pq(x, c0, 8)
+    assert all(b <= a * (1 + 1e-9) for a, b in zip(objs, objs[1:]))
+    far = c0.copy()
+    far[:, 5, :] += 1000.0
+    c1, _, _, counts = W.lloyd_step(x, far)
+    assert (counts[:, 5] == 0).all() and np.abs(c1[:, 5, :]).max() < 100.0
+    A = np.linalg.qr(r.standard_normal((32, 32)))[0].astype(np.float32)
+    A2, c2, err = W.opq_alternation(x, A, c0, 4)
+    np.testing.assert_allclose(A2 @ A2.T, np.eye(32), atol=1e-5)
+    # A2 is the best rotation for the reconstruction it was fitted to: no worse than the one it replaces
+    xp = x @ A.T
+    codes = oracle.nn_assign(np.ascontiguousarray(xp), c2)
+    rec = W.decode(codes, c2)
+    assert ((x @ A2.T - rec) ** 2).sum() <= ((x @ A.T - rec) ** 2).sum() * (1 + 1e-6)
