@@ -272,9 +272,11 @@ __device__ __forceinline__ void bulk_load_row(float* dst_smem, const float* src,
 }
 
 // Work partition: the (m, row-tile) space is flattened (m slow) and cut into G equal contiguous
-// ranges, one per persistent CTA -- balanced to one tile of SK_WARPS rows whatever M and B are.
+// ranges, one per persistent CTA -- balanced to one tile of SK_TILE rows whatever M and B are.  A tile is two
+// rows per warp (b, b + SK_WARPS): the sparse passes keep their survivor records in such row pairs.
+constexpr int SK_TILE = 2 * SK_WARPS;
 struct SkPart {
-    int64_t tpm;    // row tiles per sub-vector = ceil(B / SK_WARPS)
+    int64_t tpm;    // row tiles per sub-vector = ceil(B / SK_TILE)
     int64_t total;  // M * tpm
     int G;          // CTAs
     int S;          // max distinct sub-vectors one CTA can touch (partial slots)
@@ -286,7 +288,7 @@ constexpr int SK_MAX_CTAS_PER_SM = 4;  // partial buffer is sized for the larges
 
 static SkPart sk_partition(int64_t B, int M, int ctas_per_sm = SK_CTAS_PER_SM) {
     SkPart p;
-    p.tpm = (B + SK_WARPS - 1) / SK_WARPS;
+    p.tpm = (B + SK_TILE - 1) / SK_TILE;
     p.total = p.tpm * M;
     p.G = num_sms() * ctas_per_sm;
     const int64_t tpc = (p.total + p.G - 1) / p.G;
@@ -303,7 +305,9 @@ struct SkState {
     double* drift;    // (M,2)   {max_k, max_k - min_k} of lu - lu_build      (sparse pass)
     double* lu_build; // (M,K)   lu at the last survivor selection             (sparse pass)
     unsigned long long* cursor;  // pool allocation cursor
-    uint2* csr;          // (M,B) {pool record of the row in 16-byte units, number of survivors (0: did not fit)}
+    uint2* csr;          // (M, tiles, SK_WARPS) row-pair directory: {pool record of the pair's first row in 16-byte
+                         // units, survivors of row b | survivors of row b + SK_WARPS << 16} (0: absent / did not fit);
+                         // the second record follows the first one directly
     unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
     uint64_t pool_cap;   // pool size in 16-byte units
@@ -317,7 +321,7 @@ struct SkState {
 // so a lane of the list pass finds its own survivors contiguous, with their columns implied by the mask:
 // no column index is stored, no per-column table is gathered and the row sums stay in registers.
 constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per atomic (16 KB; a full row is 132)
-constexpr int SK_POOL_PER_ROW = 80;  // survivor pool sized for this many entries per table row on average
+constexpr int SK_POOL_PER_ROW = 112;  // survivor pool sized for this many entries per table row on average
 __host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
 __device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
 
@@ -360,7 +364,7 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
                     (uint64_t)num_sms() * SK_MAX_CTAS_PER_SM * SK_WARPS * SK_POOL_CHUNK;
     if (pool > 0xFFFFFF00ull) pool = 0xFFFFFF00ull;      // record offsets are 32-bit
     const bool csr = (K == 256);
-    const size_t o_csr = take(csr ? (size_t)M * B * 8 : 0);
+    const size_t o_csr = take(csr ? (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS * 8 : 0);
     const size_t o_U = take((size_t)M * K * 8);
     const size_t o_pool = take(csr ? (size_t)pool * 16 : 0);
     if (s) {
@@ -430,8 +434,8 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
         const int m = (int)(t / part.tpm);
         const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
         // rows of this warp inside the segment: b = b_first + SK_WARPS * i, i < nrows
-        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
-        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
         const int64_t nrows = b_first < b_stop ? (b_stop - b_first + SK_WARPS - 1) / SK_WARPS : 0;
 
         double lu[KPL], acc[KPL];
@@ -687,10 +691,12 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
     while (t < t_hi) {
         const int m = (int)(t / part.tpm);
         const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
-        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
-        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
         const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
         const float* tm = table + ((int64_t)m * B + b_first) * SP_K;   // this warp's first row
+        uint2* dir = st.csr + t * SK_WARPS + warp;                      // this warp's first row pair (tile t)
+        uint32_t pair_ptr = 0u, pair_cnt = 0u;
 
         lu_s[threadIdx.x] = lu_g[(int64_t)m * SP_K + threadIdx.x];
 #pragma unroll
@@ -777,14 +783,16 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
             //     a row is the ballot order -> deterministic sums
             {
                 const unsigned int units = sk_record_units((uint32_t)total);
-                if (units > chunk_left) {
+                // the two records of a row pair (r even, r + 1) are contiguous in the pool: only the first row of
+                // a pair may open a new chunk, and it does so unless the largest possible second record fits too
+                const bool first = (r & 1) == 0;           // segments are tile-aligned: local parity = global parity
+                if (first && units + sk_record_units(SP_K) > chunk_left) {
                     unsigned long long nb = 0;
                     if (lane == 0) nb = atomicAdd(st.cursor, (unsigned long long)SK_POOL_CHUNK);
                     chunk_base = __shfl_sync(0xffffffffu, nb, 0);
                     chunk_left = SK_POOL_CHUNK;
                 }
                 const unsigned long long off = chunk_base;
-                const int64_t row_id = (int64_t)m * B + b_first + (int64_t)r * SK_WARPS;
                 const bool fits = off + (unsigned long long)units <= st.pool_cap;
                 unsigned char* rec = st.pool + (fits ? off : 0ull) * 16ull;
                 double* pe = reinterpret_cast<double*>(rec + 64);
@@ -805,7 +813,16 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
                     const uint32_t hm = __shfl_sync(0xffffffffu, meta16, (k >> 2) & 31);
                     if (valid && fits) pe[(hm >> 8) + __popc(hm & ((1u << j) - 1u))] = q;
                 }
-                if (lane == 0) st.csr[row_id] = make_uint2((uint32_t)off, fits ? (uint32_t)total : 0u);
+                // pair directory: written with the first row, completed with the second
+                const uint32_t cnt = fits ? (uint32_t)total : 0u;
+                if (first) {
+                    pair_ptr = (uint32_t)off;
+                    pair_cnt = cnt;
+                } else {
+                    if (pair_cnt == 0u) pair_ptr = (uint32_t)off;   // first record absent: the pair starts here
+                    pair_cnt |= cnt << 16;
+                }
+                if (lane == 0) dir[(int64_t)(r >> 1) * SK_WARPS] = make_uint2(pair_ptr, pair_cnt);
                 chunk_base += (unsigned long long)units;
                 chunk_left -= units;
             }
@@ -858,11 +875,11 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
 // (a transposing butterfly: 5 exchanges for both rows) and the reciprocal are shared.  The row sums are
 // accumulated as sum_b E * rz_b and multiplied by U[k] once per segment.  Every sum has a fixed order.
 constexpr int LP_CTAS_PER_SM = 2;
-constexpr int LP_DEPTH = 4;                                         // slots (row pairs) in flight per warp
-constexpr int LP_SLOT = 2048;                                       // bytes; a pair that does not fit is read from global
+constexpr int LP_DEPTH = 3;                                         // slots (row pairs) in flight per warp
+constexpr int LP_SLOT = 3072;                                       // bytes; a pair that does not fit is read from global
 constexpr int LP_OFF_RED = SK_WARPS * LP_DEPTH * LP_SLOT;           // ring: 64 KB
 constexpr int LP_OFF_META = LP_OFF_RED + SK_WARPS * SP_K * 8;       // red : 16 KB
-constexpr int LP_OFF_BAR = LP_OFF_META + SK_WARPS * LP_DEPTH * 16;  // {ptr0, ptr1, cnt0, cnt1} per slot
+constexpr int LP_OFF_BAR = LP_OFF_META + SK_WARPS * LP_DEPTH * 8;   // directory entry per slot
 constexpr int LP_SMEM = LP_OFF_BAR + SK_WARPS * LP_DEPTH * 8;
 
 __device__ __forceinline__ uint32_t lp_record_bytes(uint32_t cnt) { return cnt ? 64u + 8u * ((cnt + 1u) & ~1u) : 0u; }
@@ -893,7 +910,7 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* my_ring = lp_smem + warp * LP_DEPTH * LP_SLOT;
     double* red_all = reinterpret_cast<double*>(lp_smem + LP_OFF_RED);
-    uint4* my_meta = reinterpret_cast<uint4*>(lp_smem + LP_OFF_META) + warp * LP_DEPTH;
+    uint2* my_meta = reinterpret_cast<uint2*>(lp_smem + LP_OFF_META) + warp * LP_DEPTH;
     const uint32_t my_bars = smem_u32(lp_smem + LP_OFF_BAR) + warp * LP_DEPTH * 8;
     const int g = blockIdx.x;
     const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
@@ -912,46 +929,38 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
         const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
         // rows of this warp inside the segment: b = b_first + SK_WARPS * i, i < nrows (the rows warp `warp` of
         // some selection CTA wrote back to back into its pool chunk)
-        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_WARPS + warp;
-        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_WARPS);
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
         const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
         const int npairs = (nrows + 1) >> 1;
-        const uint2* dir = st.csr + (int64_t)m * B + b_first;
+        const uint2* dir = st.csr + t * SK_WARPS + warp;                 // this warp's first row pair (tile t)
         double U[8], A[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             U[j] = st.U[(int64_t)m * SP_K + sp_col(lane, j)];
             A[j] = 0.0;
         }
-        // lanes 0 and 1 hold the directory entries of the two rows of the next pair to issue, one pair ahead
-        uint2 dn = make_uint2(0u, 0u);
-        auto fetch_meta = [&](int pair) {
-            const int row = 2 * pair + lane;
-            dn = (lane < 2 && row < nrows) ? dir[(int64_t)row * SK_WARPS] : make_uint2(0u, 0u);
-        };
+        // lane 0 holds the directory entry of the next pair to issue, fetched one pair ahead
         // (no proxy fence before a refill: the slot was only READ through the generic proxy, and those loads have
         //  delivered their values to the arithmetic before the __syncwarp that precedes the refill)
+        uint2 dn = make_uint2(0u, 0u);
+        auto fetch_meta = [&](int pair) {
+            if (lane == 0) dn = pair < npairs ? dir[(int64_t)pair * SK_WARPS] : make_uint2(0u, 0u);
+        };
         auto issue = [&](int pair) {
             const uint32_t slot = iss % LP_DEPTH;
-            const uint32_t ptr1 = __shfl_sync(0xffffffffu, dn.x, 1), cnt1 = __shfl_sync(0xffffffffu, dn.y, 1);
             if (lane == 0) {
-                const uint32_t ptr0 = dn.x, cnt0 = dn.y;
-                const uint32_t len0 = lp_record_bytes(cnt0), len1 = lp_record_bytes(cnt1);
-                const uint32_t bar = my_bars + 8 * slot, dst = smem_u32(my_ring + slot * LP_SLOT);
-                my_meta[slot] = make_uint4(ptr0, ptr1, cnt0, cnt1);
-                const bool staged = len0 + len1 <= (uint32_t)LP_SLOT;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                             "r"(staged ? len0 + len1 : 0u)
+                const uint32_t tot = lp_record_bytes(dn.y & 0xffffu) + lp_record_bytes(dn.y >> 16);
+                const uint32_t bar = my_bars + 8 * slot;
+                my_meta[slot] = dn;
+                const bool staged = tot <= (uint32_t)LP_SLOT;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(staged ? tot : 0u)
                              : "memory");
-                if (staged && len0)
+                if (staged && tot)
                     asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                        "l"(st.pool + (size_t)ptr0 * 16), "r"(len0), "r"(bar)
-                        : "memory");
-                if (staged && len1)
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + len0),
-                        "l"(st.pool + (size_t)ptr1 * 16), "r"(len1), "r"(bar)
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            smem_u32(my_ring + slot * LP_SLOT)),
+                        "l"(st.pool + (size_t)dn.x * 16), "r"(tot), "r"(bar)
                         : "memory");
             }
             fetch_meta(pair + 1);
@@ -964,22 +973,23 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
         for (int q = 0; q < npairs; ++q) {
             const uint32_t slot = seq % LP_DEPTH;
             mbar_wait(my_bars + 8 * slot, (seq / LP_DEPTH) & 1u);
-            const uint4 mt = my_meta[slot];                     // {ptr0, ptr1, cnt0, cnt1}
-            const uint32_t len0 = lp_record_bytes(mt.z), len1 = lp_record_bytes(mt.w);
+            const uint2 mt = my_meta[slot];                     // {record of the pair, cnt0 | cnt1 << 16}
+            const uint32_t cnt0 = mt.y & 0xffffu, cnt1 = mt.y >> 16;
+            const uint32_t len0 = lp_record_bytes(cnt0), len1 = lp_record_bytes(cnt1);
             uint32_t hm0 = 0u, hm1 = 0u;
             double e0[8], e1[8], s0, s1;
             if (len0 + len1 <= (uint32_t)LP_SLOT) {             // (two code paths: shared / global address space)
                 const unsigned char* rec0 = my_ring + slot * LP_SLOT;
                 const unsigned char* rec1 = rec0 + len0;
-                if (mt.z) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
-                if (mt.w) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+                if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+                if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
                 s0 = lp_gather_row(rec0, hm0, U, e0);
                 s1 = lp_gather_row(rec1, hm1, U, e1);
             } else {                                            // oversized pair (rare): straight from the pool
                 const unsigned char* rec0 = st.pool + (size_t)mt.x * 16;
-                const unsigned char* rec1 = st.pool + (size_t)mt.y * 16;
-                if (mt.z) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
-                if (mt.w) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+                const unsigned char* rec1 = rec0 + len0;
+                if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+                if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
                 s0 = lp_gather_row(rec0, hm0, U, e0);
                 s1 = lp_gather_row(rec1, hm1, U, e1);
             }
@@ -994,7 +1004,7 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
             a += __shfl_xor_sync(0xffffffffu, a, 4);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             a += __shfl_xor_sync(0xffffffffu, a, 1);
-            const bool live = (hi ? mt.w : mt.z) != 0u;
+            const bool live = (hi ? cnt1 : cnt0) != 0u;
             if (live && (!(a > 0.0) || !isfinite(a))) bad |= RC_FLAG_NONFINITE;
             const double rz = live ? __drcp_rn(a) * rBg : 0.0;      // Q / (B_global * column sum)  (:162-163)
             const double rz0 = __shfl_sync(0xffffffffu, rz, 0), rz1 = __shfl_sync(0xffffffffu, rz, 16);
@@ -1194,14 +1204,19 @@ sinkhorn_expand_kernel(const float* __restrict__ table, int64_t B, int M, int K,
         Q[((int64_t)m * K + k) * B + b] = exp2(fma(-(double)row[k], scale2, lu[k]) - mx) / s;
 }
 
-__global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t rows, unsigned long long* out) {
+__global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t pairs, unsigned long long* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    const unsigned int c = csr[i].y;
-    atomicAdd(out + 0, (unsigned long long)c);
-    atomicMax(out + 1, (unsigned long long)c);
-    atomicAdd(out + 2, 1ull);
-    atomicAdd(out + 3 + min(c >> 3, 32u), 1ull);
+    if (i >= pairs) return;
+    const uint32_t cc = csr[i].y;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const unsigned int c = h ? (cc >> 16) : (cc & 0xffffu);
+        if (c == 0) continue;
+        atomicAdd(out + 0, (unsigned long long)c);
+        atomicMax(out + 1, (unsigned long long)c);
+        atomicAdd(out + 2, 1ull);
+        atomicAdd(out + 3 + min(c >> 3, 32u), 1ull);
+    }
 }
 
 __global__ void fill_f64_kernel(double* p, int64_t n, double v) {
@@ -1362,8 +1377,10 @@ RC_API int rc_dist_table(const float* x, int64_t ldx, const float* centroids, in
     return rc;
 }
 
-static int sk_reset(const SkState& s, int M, int K, cudaStream_t st) {
+static int sk_reset(const SkState& s, int64_t B, int M, int K, cudaStream_t st) {
     const int64_t n = (int64_t)M * K;
+    if (K == SP_K)   // pair directory: entries of rows past B stay empty
+        RC_CUDA(cudaMemsetAsync(s.csr, 0, (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS * sizeof(uint2), st));
     fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, n, 0.0);
     RC_CHECK_LAUNCH("fill_f64_kernel");
     fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu_build, n, 0.0);
@@ -1404,7 +1421,7 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    rc = sk_reset(s, M, K, st);
+    rc = sk_reset(s, B, M, K, st);
     if (rc) return rc;
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
@@ -1427,7 +1444,7 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    rc = sk_reset(s, M, K, st);
+    rc = sk_reset(s, B, M, K, st);
     if (rc) return rc;
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
@@ -1496,8 +1513,8 @@ RC_API int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t*
     SkState s;
     sk_layout(B, M, K, p, state, &s);
     RC_CUDA(cudaMemsetAsync(out, 0, 36 * sizeof(int64_t), st));
-    const int64_t rows = (int64_t)M * B;
-    list_stats_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(s.csr, rows, (unsigned long long*)out);
+    const int64_t pairs = (int64_t)M * p.tpm * SK_WARPS;
+    list_stats_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(s.csr, pairs, (unsigned long long*)out);
     RC_CHECK_LAUNCH("list_stats_kernel");
     return RC_OK;
 }
