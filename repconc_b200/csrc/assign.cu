@@ -262,6 +262,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// Programmatic dependent launch: the kernels of the solve loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled while this one
+// drains.  Every such kernel calls pdl_wait() before it touches anything a predecessor wrote (or may still
+// read) -- it returns once ALL prerequisite grids have completed and flushed -- and only then lets its own
+// dependents be scheduled.  Both are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // one table row: global -> shared, 1-D bulk copy (TMA engine), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load_row(float* dst_smem, const float* src, uint32_t bytes, uint32_t bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -661,6 +668,8 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
                             SkPart part, const double* __restrict__ lu_g, const double* __restrict__ drift,
                             int force, SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char sp_smem[];
+    pdl_wait();
+    pdl_launch_dependents();
     if (!csr_reselect(drift, M, force)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* my_ring = reinterpret_cast<float*>(sp_smem) + warp * SK_DEPTH * SP_K;
@@ -906,6 +915,8 @@ __global__ void __launch_bounds__(SK_THREADS, LP_CTAS_PER_SM)
 sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const double* __restrict__ drift, int force,
                           SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char lp_smem[];
+    pdl_wait();
+    pdl_launch_dependents();
     if (csr_reselect(drift, M, force)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* my_ring = lp_smem + warp * LP_DEPTH * LP_SLOT;
@@ -1090,6 +1101,8 @@ __global__ void __launch_bounds__(256)
 sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part_in, SkPart part_list, int K,
                        double* __restrict__ P, int csr_mode, int M, int force, SkState st) {
     __shared__ int s_off[SK_RED_LIST];
+    pdl_wait();
+    pdl_launch_dependents();
     sk_reduce_block(partial, part_in, part_list, K, P, csr_mode, M, force, st, s_off);
 }
 
@@ -1164,6 +1177,8 @@ sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, co
                        double* __restrict__ U, int32_t* __restrict__ flags) {
     __shared__ double red_mx[8], red_mn[8];
     __shared__ double s_dmax;
+    pdl_wait();
+    pdl_launch_dependents();
     sk_update_block(lu, P, lu_build, K, Kd, check_mass, slack, drift, U, flags, red_mx, red_mn, &s_dmax);
 }
 
@@ -1175,6 +1190,8 @@ sinkhorn_reduce_update_kernel(const double* __restrict__ partial, SkPart part_in
     __shared__ int s_off[SK_RED_LIST];
     __shared__ double red_mx[8], red_mn[8];
     __shared__ double s_dmax;
+    pdl_wait();
+    pdl_launch_dependents();
     sk_reduce_block(partial, part_in, part_list, K, st.P, csr_mode, M, force, st, s_off);
     __syncthreads();   // P[m,:] and lu_build[m,:] of this block are final (each element is re-read by its writer)
     sk_update_block(st.lu, st.P, st.lu_build, K, (double)K, check_mass, st.slack, st.drift, st.U, flags, red_mx,
@@ -1224,6 +1241,32 @@ __global__ void fill_f64_kernel(double* p, int64_t n, double v) {
     if (i < n) p[i] = v;
 }
 
+static bool use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RC_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// <<<grid, block, smem, st>>> with programmatic stream serialization (see pdl_wait)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int MODE>
 static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, int M, int K, double eps,
                        const SkPart& p, const SkState& s, int64_t* mb, uint8_t* u8, int32_t* flags,
@@ -1260,7 +1303,8 @@ static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, 
 
 static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaStream_t st, int csr_mode = 0,
                          int force = 0, const SkPart* p_list = nullptr) {
-    sinkhorn_reduce_kernel<<<M, 256, 0, st>>>(s.partial, p, p_list ? *p_list : p, K, s.P, csr_mode, M, force, s);
+    RC_CUDA(launch_chain(sinkhorn_reduce_kernel, (unsigned)M, 256u, 0, st, s.partial, p, p_list ? *p_list : p, K, s.P,
+                         csr_mode, M, force, s));
     RC_CHECK_LAUNCH("sinkhorn_reduce_kernel");
     return RC_OK;
 }
@@ -1268,8 +1312,8 @@ static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaSt
 static int launch_update(const SkState& s, int M, int K, double Bg, int check_mass, int32_t* flags,
                          cudaStream_t st) {
     (void)Bg;
-    sinkhorn_update_kernel<<<M, 256, 0, st>>>(s.lu, s.P, s.lu_build, K, (double)K, check_mass, s.slack, s.drift, s.U,
-                                              flags);
+    RC_CUDA(launch_chain(sinkhorn_update_kernel, (unsigned)M, 256u, 0, st, s.lu, s.P, s.lu_build, K, (double)K, check_mass,
+                         s.slack, s.drift, s.U, flags));
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
 }
@@ -1286,10 +1330,11 @@ static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, i
     }
     const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM), pl = sk_partition(B, M, LP_CTAS_PER_SM);
     const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
-    sinkhorn_step_sparse_kernel<<<ps.G, SK_THREADS, SP_SMEM, st>>>(table, B, rBg, M, scale2, ps, s.lu, s.drift, force, s,
-                                                                  s.partial, flags);
+    RC_CUDA(launch_chain(sinkhorn_step_sparse_kernel, ps.G, SK_THREADS, SP_SMEM, st, table, B, rBg, M, scale2, ps, s.lu,
+                         s.drift, force, s, s.partial, flags));
     RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
-    sinkhorn_step_list_kernel<<<pl.G, SK_THREADS, LP_SMEM, st>>>(B, rBg, M, pl, s.drift, force, s, s.partial, flags);
+    RC_CUDA(launch_chain(sinkhorn_step_list_kernel, pl.G, SK_THREADS, LP_SMEM, st, B, rBg, M, pl, s.drift, force, s,
+                         s.partial, flags));
     RC_CHECK_LAUNCH("sinkhorn_step_list_kernel");
     *ps_out = ps;
     *pl_out = pl;
@@ -1460,8 +1505,8 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
     SkPart pin = p, plist = p;
     for (int it = 0; it < iters; ++it) {
         const bool last = it == iters - 1;
-        sinkhorn_reduce_update_kernel<<<M, 256, 0, st>>>(s.partial, pin, plist, K, csr_mode, M, force,
-                                                         (!last && sparse && it > 0) ? 1 : 0, s, flags);
+        RC_CUDA(launch_chain(sinkhorn_reduce_update_kernel, (unsigned)M, 256u, 0, st, s.partial, pin, plist, K, csr_mode,
+                             M, force, (!last && sparse && it > 0) ? 1 : 0, s, flags));
         RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
         if (last) break;
         if (sparse) {
