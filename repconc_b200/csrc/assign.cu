@@ -869,6 +869,130 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
     if (bad) atomicOr(flags, bad);
 }
 
+// FINISH for K == 256: argmax_k (a + lu[k]) per table row with an fp32 pre-filter.  The warp evaluates the 256
+// candidates in fp32 (error < 2e-4 log2 units: |a| <= 1.45/eps, |lu| of the same order), keeps those within
+// FS_TOL of the fp32 maximum and -- only if more than one is left -- evaluates the kept ones in fp64 exactly as
+// the dense FINISH pass does (exact ties -> smallest k).  A row whose fp32 maximum is not an ordinary number
+// (NaN anywhere, overflow range) takes the full fp64 evaluation with the dense pass's NaN / flag semantics.
+// HBM-bound: one read of the table.
+constexpr int FS_CTAS_PER_SM = 4;
+constexpr float FS_TOL = 0.01f;
+
+__global__ void __launch_bounds__(SK_THREADS, FS_CTAS_PER_SM)
+sinkhorn_finish_sparse_kernel(const float* __restrict__ table, int64_t B, int M, double scale2, SkPart part,
+                              const double* __restrict__ lu_g, int64_t* __restrict__ codes_mb,
+                              uint8_t* __restrict__ codes_u8, int32_t* __restrict__ flags) {
+    __shared__ __align__(128) float ring[SK_WARPS * SK_DEPTH * SP_K];
+    __shared__ double lu_s[SP_K];
+    __shared__ __align__(8) unsigned long long bars[SK_WARPS * SK_DEPTH];
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* my_ring = ring + warp * SK_DEPTH * SP_K;
+    const uint32_t my_bars = smem_u32(bars + warp * SK_DEPTH);
+    const int g = blockIdx.x;
+    const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
+    if (t_lo >= t_hi) return;
+    int bad = 0;
+    uint32_t seq = 0;
+    if (lane == 0)
+        for (int d = 0; d < SK_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
+    fence_barrier_init();
+    __syncwarp();
+    const float scale32 = (float)scale2;
+    const uint32_t row_bytes = SP_K * 4u;
+
+    int64_t t = t_lo;
+    while (t < t_hi) {
+        const int m = (int)(t / part.tpm);
+        const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
+        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
+        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
+        const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
+        const float* tm = table + ((int64_t)m * B + b_first) * SP_K;
+        __syncthreads();                                     // the previous segment's readers of lu_s are done
+        lu_s[threadIdx.x] = lu_g[(int64_t)m * SP_K + threadIdx.x];
+        __syncthreads();
+        float lu32[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lu32[j] = (float)lu_s[sp_col(lane, j)];
+        if (lane == 0) {
+            const int pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
+            for (int d = 0; d < pre; ++d) {
+                const uint32_t slot = (seq + (uint32_t)d) % SK_DEPTH;
+                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)d * SK_WARPS * SP_K, row_bytes, my_bars + 8 * slot);
+            }
+        }
+        for (int r = 0; r < nrows; ++r) {
+            const uint32_t slot = seq % SK_DEPTH;
+            mbar_wait(my_bars + 8 * slot, (seq / SK_DEPTH) & 1u);
+            const float* src = my_ring + slot * SP_K;
+            const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
+            const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            __syncwarp();                                    // the slot is in registers: refill it
+            if (lane == 0 && r + SK_DEPTH < nrows)
+                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
+                              my_bars + 8 * slot);
+            ++seq;
+            float wf[8];
+            float mx = -INFINITY;
+            bool odd = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                wf[j] = fmaf(-dv[j], scale32, lu32[j]);
+                odd |= wf[j] != wf[j];
+                mx = fmaxf(mx, wf[j]);
+            }
+            mx = warp_max(mx);
+            const bool slow = __any_sync(0xffffffffu, odd) || !(mx < 1000.0f) || !(mx > -3.0e38f);
+            uint32_t cand = 0xffu;
+            int code = -1;
+            if (!slow) {
+                const float cut = mx - FS_TOL;
+                cand = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cand |= (wf[j] >= cut ? 1u : 0u) << j;
+                const uint32_t bal = __ballot_sync(0xffffffffu, cand != 0u);
+                const int owner = __ffs(bal) - 1;
+                const int mine = __popc(cand) == 1 ? sp_col(lane, __ffs(cand) - 1) : -1;
+                if ((bal & (bal - 1u)) == 0u) code = __shfl_sync(0xffffffffu, mine, owner);   // one lane has candidates
+            }
+            if (code < 0) {                                  // (warp-uniform) several candidates, or an odd row
+                double w[8];
+                double best = -INFINITY;
+                bool has_nan = false;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    w[j] = -INFINITY;
+                    if ((cand >> j) & 1u) {
+                        w[j] = fma(-(double)dv[j], scale2, lu_s[sp_col(lane, j)]);
+                        if (w[j] != w[j]) has_nan = true;
+                        else best = fmax(best, w[j]);
+                        if (!(w[j] < 1024.0)) bad |= RC_FLAG_NONFINITE;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+                const bool any_nan = __any_sync(0xffffffffu, has_nan);
+                int bk = SP_K;
+#pragma unroll
+                for (int j = 7; j >= 0; --j)
+                    if (((cand >> j) & 1u) && (any_nan ? (w[j] != w[j]) : (w[j] >= best))) bk = sp_col(lane, j);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) bk = min(bk, __shfl_xor_sync(0xffffffffu, bk, o));
+                code = bk >= SP_K ? 0 : bk;                   // all -inf: torch.argmax returns the first index
+            }
+            if (lane == 0) {
+                const int64_t b = b_first + (int64_t)r * SK_WARPS;
+                if (codes_mb) codes_mb[(int64_t)m * B + b] = code;
+                if (codes_u8) codes_u8[b * M + m] = (uint8_t)code;
+            }
+        }
+        t = t_end;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
 // Iteration on the survivor lists alone (see the comment above sinkhorn_step_sparse_kernel).
 // A record carries E = 2^(w - rowmax) as evaluated (fp64) by the selection pass; since then only lu moved, so
 // the element's current value is E * 2^(lu[k] - lu_build[k]) -- up to a per-row constant that the column
@@ -1350,6 +1474,19 @@ static bool sinkhorn_dense() {
     return g_sinkhorn_dense == 1;
 }
 
+static int launch_finish(const float* table, int64_t B, int M, int K, double eps, const SkPart& p, const SkState& s,
+                         int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, cudaStream_t st) {
+    if (K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense()) {
+        const SkPart pf = sk_partition(B, M, FS_CTAS_PER_SM);
+        RC_CUDA(launch_chain(sinkhorn_finish_sparse_kernel, (unsigned)pf.G, (unsigned)SK_THREADS, 0, st, table, B, M,
+                             RC_LOG2E / eps, pf, (const double*)s.lu, codes_mb, codes_u8, flags));
+        RC_CHECK_LAUNCH("sinkhorn_finish_sparse_kernel");
+        return RC_OK;
+    }
+    return launch_pass<SK_FINISH>(const_cast<float*>(table), nullptr, B, (double)B, M, K, eps, p, s, codes_mb, codes_u8,
+                                  flags, st);
+}
+
 }  // namespace rc
 
 using namespace rc;
@@ -1519,7 +1656,7 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
             if (rc) return rc;
         }
     }
-    return launch_pass<SK_FINISH>(table, nullptr, B, (double)B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
+    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
 }
 
 RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
@@ -1605,6 +1742,5 @@ RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, i
         rc = launch_update(s, M, K, (double)B_global, 0, flags, st);
         if (rc) return rc;
     }
-    return launch_pass<SK_FINISH>(const_cast<float*>(table), nullptr, B, (double)B, M, K, eps, p, s, codes_mb,
-                                  codes_u8, flags, st);
+    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
 }

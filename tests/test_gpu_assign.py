@@ -269,3 +269,44 @@ def test_list_pass_oversized_rows():
     assert torch.equal(out[False][0], out[True][0])
     rel = ((out[False][1] - out[True][1]).abs() / out[True][1]).max().item()
     assert rel < 1e-12, rel
+
+
+def test_sparse_finish_ties_and_odd_rows_match_dense():
+    """The fp32-filtered FINISH (K = 256) and the dense FINISH agree on exact ties (duplicate centroids ->
+    smallest k), on rows with several near-maximal candidates and on NaN rows (NaN counts as largest)."""
+    from repconc_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    B, M, ds = 1500, 6, 16
+    x = torch.randn((B, M * ds), generator=gen, device="cuda")
+    c = torch.randn((M, 256, ds), generator=gen, device="cuda")
+    c[:, 200:256] = c[:, 100:156]                       # 56 exact duplicates per sub-vector
+    c[:, 7] = c[:, 3] + 1e-6                            # and one near-duplicate
+    out = {}
+    for T in (0, 6):
+        for dense in (False, True):
+            k = ops.CudaAssignKernels(x, c)
+            prev = k.set_dense(dense)
+            try:
+                k.table()
+                out[(T, dense)] = k.solve(0.003, T).clone()
+            finally:
+                k.set_dense(prev)
+        assert torch.equal(out[(T, False)], out[(T, True)]), T
+    assert (out[(6, False)] < 200).all()                # ties resolve to the smaller index
+    # NaN rows: poison a few table entries after the table is built (begin propagates them)
+    res = {}
+    for dense in (False, True):
+        k = ops.CudaAssignKernels(x, c)
+        prev = k.set_dense(dense)
+        try:
+            k.table()
+            k.begin(0.003)
+            k.tab[2, 17, 33] = float("nan")
+            k.tab[4, 900, 250] = float("nan")
+            k.tab[4, 900, 12] = float("nan")
+            res[dense] = (k.finish(0.003, False).clone(), k.read_flags())
+        finally:
+            k.set_dense(prev)
+    assert torch.equal(res[False][0], res[True][0])
+    assert res[False][0][17, 2] == 33 and res[False][0][900, 4] == 12
+    assert res[False][1] == res[True][1] and res[False][1] & 1
