@@ -328,11 +328,11 @@ struct SkState {
 // so a lane of the list pass finds its own survivors contiguous, with their columns implied by the mask:
 // no column index is stored, no per-column table is gathered and the row sums stay in registers.
 constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per atomic (16 KB; a full row is 132)
-constexpr int SK_POOL_PER_ROW = 112;  // survivor pool sized for this many entries per table row on average
+constexpr int SK_POOL_PER_ROW = 160;  // survivor pool sized for this many entries per table row on average
 __host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
 __device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
 
-constexpr double SK_SLACK = 24.0;        // default extra selection depth = admissible drift of lu between selections
+constexpr double SK_SLACK = 40.0;        // default extra selection depth = admissible drift of lu between selections
 // (run-time tunable for experiments: env RC_SINKHORN_SLACK; deeper selection = longer lists, fewer re-selections;
 //  the error bound depends on SK_MARGIN only)
 static double sk_slack() {
