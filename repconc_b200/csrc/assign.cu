@@ -313,7 +313,7 @@ struct SkState {
     double* lu_build; // (M,K)   lu at the last survivor selection             (sparse pass)
     unsigned long long* cursor;  // pool allocation cursor
     uint2* csr;          // (M, tiles, SK_WARPS) row-pair directory: {pool record of the pair's first row in 16-byte
-                         // units, survivors of row b | survivors of row b + SK_WARPS << 16} (0: absent / did not fit);
+                         // units, sk_dir_word(survivors of row b, of row b + SK_WARPS)} (0: absent / did not fit);
                          // the second record follows the first one directly
     unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
@@ -331,6 +331,20 @@ constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per 
 constexpr int SK_POOL_PER_ROW = 160;  // survivor pool sized for this many entries per table row on average
 __host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
 __device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
+// Row-pair directory word: bytes of the first record (0 = absent) | bytes of both records << 12 | odd-count
+// bits (25, 26) so that the exact survivor counts can be recovered (diagnostics).  A record is
+// 64 + 8 * (count rounded up to even) bytes <= 2112.
+__host__ __device__ constexpr uint32_t sk_record_bytes(uint32_t cnt) { return cnt ? 64u + 8u * ((cnt + 1u) & ~1u) : 0u; }
+__host__ __device__ constexpr uint32_t sk_dir_word(uint32_t cnt0, uint32_t cnt1) {
+    return sk_record_bytes(cnt0) | ((sk_record_bytes(cnt0) + sk_record_bytes(cnt1)) << 12) | ((cnt0 & 1u) << 25) |
+           ((cnt1 & 1u) << 26);
+}
+__host__ __device__ constexpr uint32_t sk_dir_len0(uint32_t w) { return w & 0xfffu; }
+__host__ __device__ constexpr uint32_t sk_dir_total(uint32_t w) { return (w >> 12) & 0x1fffu; }
+__host__ __device__ constexpr uint32_t sk_dir_cnt(uint32_t w, int h) {
+    const uint32_t len = h ? sk_dir_total(w) - sk_dir_len0(w) : sk_dir_len0(w);
+    return len ? (len - 64u) / 8u - ((w >> (25 + h)) & 1u) : 0u;
+}
 
 constexpr double SK_SLACK = 40.0;        // default extra selection depth = admissible drift of lu between selections
 // (run-time tunable for experiments: env RC_SINKHORN_SLACK; deeper selection = longer lists, fewer re-selections;
@@ -824,14 +838,16 @@ sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double r
                 }
                 // pair directory: written with the first row, completed with the second
                 const uint32_t cnt = fits ? (uint32_t)total : 0u;
+                uint32_t word;
                 if (first) {
                     pair_ptr = (uint32_t)off;
                     pair_cnt = cnt;
+                    word = sk_dir_word(cnt, 0u);
                 } else {
                     if (pair_cnt == 0u) pair_ptr = (uint32_t)off;   // first record absent: the pair starts here
-                    pair_cnt |= cnt << 16;
+                    word = sk_dir_word(pair_cnt, cnt);
                 }
-                if (lane == 0) dir[(int64_t)(r >> 1) * SK_WARPS] = make_uint2(pair_ptr, pair_cnt);
+                if (lane == 0) dir[(int64_t)(r >> 1) * SK_WARPS] = make_uint2(pair_ptr, word);
                 chunk_base += (unsigned long long)units;
                 chunk_left -= units;
             }
@@ -1015,7 +1031,6 @@ constexpr int LP_OFF_META = LP_OFF_RED + SK_WARPS * SP_K * 8;       // red : 16 
 constexpr int LP_OFF_BAR = LP_OFF_META + SK_WARPS * LP_DEPTH * 8;   // directory entry per slot
 constexpr int LP_SMEM = LP_OFF_BAR + SK_WARPS * LP_DEPTH * 8;
 
-__device__ __forceinline__ uint32_t lp_record_bytes(uint32_t cnt) { return cnt ? 64u + 8u * ((cnt + 1u) & ~1u) : 0u; }
 
 // this lane's survivors of one row: e[j] = E of column k(lane,j) or 0; returns sum_j e[j] * U[j]
 __device__ __forceinline__ double lp_gather_row(const unsigned char* rec, uint32_t hm, const double (&U)[8],
@@ -1052,7 +1067,8 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
     if (t_lo >= t_hi) return;
     const int m_first = (int)(t_lo / part.tpm);
     int bad = 0;
-    uint32_t seq = 0, iss = 0;   // row pairs consumed / issued by this warp since kernel start
+    // ring positions of this warp: next slot to consume (and its mbarrier phase), next slot to fill
+    uint32_t c_slot = 0, c_phase = 0, i_slot = 0;
     if (lane == 0)
         for (int d = 0; d < LP_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
     fence_barrier_init();
@@ -1083,9 +1099,9 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
             if (lane == 0) dn = pair < npairs ? dir[(int64_t)pair * SK_WARPS] : make_uint2(0u, 0u);
         };
         auto issue = [&](int pair) {
-            const uint32_t slot = iss % LP_DEPTH;
+            const uint32_t slot = i_slot;
             if (lane == 0) {
-                const uint32_t tot = lp_record_bytes(dn.y & 0xffffu) + lp_record_bytes(dn.y >> 16);
+                const uint32_t tot = sk_dir_total(dn.y);
                 const uint32_t bar = my_bars + 8 * slot;
                 my_meta[slot] = dn;
                 const bool staged = tot <= (uint32_t)LP_SLOT;
@@ -1099,21 +1115,21 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
                         : "memory");
             }
             fetch_meta(pair + 1);
-            ++iss;
+            i_slot = i_slot + 1 == LP_DEPTH ? 0u : i_slot + 1;
         };
         fetch_meta(0);
         for (int q = 0; q < npairs && q < LP_DEPTH; ++q) issue(q);
         __syncwarp();
 
         for (int q = 0; q < npairs; ++q) {
-            const uint32_t slot = seq % LP_DEPTH;
-            mbar_wait(my_bars + 8 * slot, (seq / LP_DEPTH) & 1u);
-            const uint2 mt = my_meta[slot];                     // {record of the pair, cnt0 | cnt1 << 16}
-            const uint32_t cnt0 = mt.y & 0xffffu, cnt1 = mt.y >> 16;
-            const uint32_t len0 = lp_record_bytes(cnt0), len1 = lp_record_bytes(cnt1);
+            const uint32_t slot = c_slot;
+            mbar_wait(my_bars + 8 * slot, c_phase);
+            const uint2 mt = my_meta[slot];                     // {record of the pair, sk_dir_word}
+            const uint32_t len0 = sk_dir_len0(mt.y), tot = sk_dir_total(mt.y);
+            const uint32_t cnt0 = len0, cnt1 = tot - len0;      // (only their being zero / non-zero is used below)
             uint32_t hm0 = 0u, hm1 = 0u;
             double e0[8], e1[8], s0, s1;
-            if (len0 + len1 <= (uint32_t)LP_SLOT) {             // (two code paths: shared / global address space)
+            if (tot <= (uint32_t)LP_SLOT) {                     // (two code paths: shared / global address space)
                 const unsigned char* rec0 = my_ring + slot * LP_SLOT;
                 const unsigned char* rec1 = rec0 + len0;
                 if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
@@ -1148,7 +1164,8 @@ sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const doubl
                 A[j] = fma(e0[j], rz0, A[j]);
                 A[j] = fma(e1[j], rz1, A[j]);
             }
-            ++seq;
+            c_slot = c_slot + 1 == LP_DEPTH ? 0u : c_slot + 1;
+            c_phase ^= c_slot == 0 ? 1u : 0u;
         }
         // row sums of the segment: warp 0..7 in order (deterministic)
         {
@@ -1351,7 +1368,7 @@ __global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t pairs, 
     const uint32_t cc = csr[i].y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const unsigned int c = h ? (cc >> 16) : (cc & 0xffffu);
+        const unsigned int c = sk_dir_cnt(cc, h);
         if (c == 0) continue;
         atomicAdd(out + 0, (unsigned long long)c);
         atomicMax(out + 1, (unsigned long long)c);
