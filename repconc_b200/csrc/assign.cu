@@ -65,7 +65,14 @@ nn_assign_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
         __syncthreads();
         for (int kk = 0; kk < kn; ++kk) {
             const float* ck = cs + kk * DS;
-            const float d = sum_aten_order<DS>([&](int j) { return sqdiff(xr[j], ck[j]); });
+            float d;
+            if constexpr (DS % 8 == 0) {
+                const f32x2_t* ck2 = reinterpret_cast<const f32x2_t*>(ck);
+                d = sqdist_aten_order_packed<DS>([&](int p) { return pk2(xr[2 * p], xr[2 * p + 1]); },
+                                                 [&](int p) { return ck2[p]; });
+            } else {
+                d = sum_aten_order<DS>([&](int j) { return sqdiff(xr[j], ck[j]); });
+            }
             const int k = k0 + kk;
             // torch.argmin: first minimum, NaN counts as smallest
             if (k == 0 || d < best || (d != d && best == best)) {
@@ -162,7 +169,14 @@ dist_table_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
         float* out = table + ((int64_t)m * B + b0) * K + k;
         for (int r = 0; r < rows; ++r) {
             const float* xr = xs + r * DS;
-            const float d = sum_aten_order<DS>([&](int j) { return sqdiff(xr[j], cr[j]); });
+            float d;
+            if constexpr (DS % 8 == 0) {
+                const f32x2_t* xr2 = reinterpret_cast<const f32x2_t*>(xr);
+                d = sqdist_aten_order_packed<DS>([&](int p) { return xr2[p]; },
+                                                 [&](int p) { return pk2(cr[2 * p], cr[2 * p + 1]); });
+            } else {
+                d = sum_aten_order<DS>([&](int j) { return sqdiff(xr[j], cr[j]); });
+            }
             out[(int64_t)r * K] = d;
             if (d != d) has_nan = true;
             else {

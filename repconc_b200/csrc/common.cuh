@@ -167,6 +167,79 @@ __device__ __forceinline__ float sqdiff(float x, float c) {
     return __fmul_rn(d, d);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed fp32 (Blackwell FADD2 / FFMA2: two IEEE-rn fp32 operations per instruction).  The distance kernels
+// are bound by instruction issue (3 non-contractable ops per dimension); the packed forms halve the count
+// without touching the arithmetic: every lane of sub/add.rn.f32x2 is the scalar rn operation, and the
+// square is fma.rn(d, d, +0) = rn(d*d) -- one rounding, identical to mul.rn (a square is never -0).
+// (mul.rn.f32x2 followed by add.rn.f32x2 is NOT used: ptxas contracts that pair into one FFMA2.)
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t add2_rn(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t sq2_rn(f32x2_t d) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(d), "l"(0ull));
+    return r;
+}
+
+// sum_j (x[j] - c[j])^2 in the order of sum_aten_order<N> for N a multiple of 8, two elements per instruction.
+// x2(p) / c2(p) return elements (2p, 2p+1) packed.  Accumulators that are still exactly +0 are assigned
+// instead of added to (0 + v == v), everything else is the scalar sequence operation for operation.
+template <int N, typename FX, typename FC>
+__device__ __forceinline__ float sqdist_aten_order_packed(FX x2, FC c2) {
+    static_assert(N % 8 == 0 && N >= 8 && N < 512, "packed path: N = 8, 16, 24, ...");
+    constexpr int NV = N / 8, NI = NV / 4;
+    f32x2_t acc[4][4];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int e = ((i * 4 + k) * 8) / 2 + p;
+                const f32x2_t t = sq2_rn(sub2_rn(x2(e), c2(e)));
+                acc[k][p] = i == 0 ? t : add2_rn(acc[k][p], t);
+            }
+#pragma unroll
+    for (int i = NI * 4; i < NV; ++i)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int e = (i * 8) / 2 + p;
+            const f32x2_t t = sq2_rn(sub2_rn(x2(e), c2(e)));
+            acc[0][p] = (NI == 0 && i == 0) ? t : add2_rn(acc[0][p], t);
+        }
+    if (NI > 0) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[0][p] = add2_rn(acc[0][p], acc[k][p]);
+    }
+    float a[8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) unpk2(acc[0][p], a[2 * p], a[2 * p + 1]);
+    float fin = a[0];                                   // 0 + a[0]
+#pragma unroll
+    for (int l = 1; l < 8; ++l) fin = __fadd_rn(fin, a[l]);
+    return fin;
+}
+
 // warp reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
