@@ -82,6 +82,13 @@ def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np
     """evaluate_repconc.py:188-206."""
     all_topk_scores, all_topk_ids = [], []
     iterations = math.ceil(len(query_ids) / batch_size)
+    if (iterations > 1 and isinstance(index, faiss.GpuIndexPQ) and isinstance(query_embeds, np.ndarray)
+            and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
+        # same batches (np.array_split, :193-197), searched back to back with the copy-back of one batch
+        # overlapping the scan of the next
+        scores, ids = index.search_batches(np.array_split(query_embeds, iterations), topk, corpus_ids=corpus_ids)
+        assert len(query_ids) == len(scores) == len(ids)
+        return scores, ids
     for query_id_iter, query_embeds_iter in tqdm(zip(
         np.array_split(query_ids, iterations),
         np.array_split(query_embeds, iterations),

@@ -286,6 +286,107 @@ class GpuIndexPQ:
         return hs.numpy().copy(), hi.numpy().copy()
 
 
+    def search_batches(self, batches, k, corpus_ids=None):
+        """Pipelined `search` over a list of host query arrays (the loop of evaluate_repconc.batch_search,
+        `:193-203`): while the GPU scans batch i+1, the results of batch i travel device -> pinned host on a copy
+        stream and are written into their slice of the preallocated output.  Returns (scores (n,k) fp32,
+        ids (n,k) int64) for the concatenated batches -- value for value what per-batch `search` calls give."""
+        k = int(k)
+        sizes = [int(len(b)) for b in batches]
+        n = sum(sizes)
+        out_s = np.empty((n, k), np.float32)
+        out_i = np.empty((n, k), np.int64)
+        if n == 0:
+            return out_s, out_i
+        with torch.cuda.device(self.device):
+            ids_dev = self._resident_ids(corpus_ids) if corpus_ids is not None else None
+            if corpus_ids is not None and ids_dev is None:
+                raise TypeError("search_batches: corpus_ids must be an int64 array")
+            compute = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            # rc_adc_search returns only when the scan has finished (it reads the survivor counters back), so the
+            # copy-back of batch i is drained by a helper thread while the caller's thread sits in the scan of
+            # batch i+1 (ctypes and numpy's block copies both release the GIL).
+            if getattr(self, "_drain_pool", None) is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._drain_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="repconc-drain")
+            busy = [None, None]     # per staging slot: future of the drain that still reads it
+            lo = 0
+
+            def drain(plo, phi, slot, ev, _keep):
+                ev.synchronize()
+                out_s[plo:phi] = self._pinned(f"s{slot}", (phi - plo, k), torch.float32).numpy()
+                out_i[plo:phi] = self._pinned(f"i{slot}", (phi - plo, k), torch.int64).numpy()
+
+            trace = getattr(self, "_trace", None)      # debugging: list that receives (label, seconds) marks
+            import time as _time
+
+            def mark(label):
+                if trace is not None:
+                    trace.append((label, _time.perf_counter()))
+
+            # all queries go to the device up front (one staging pass + one DMA, in groups of <= 256 MB): the
+            # caller's thread then does no large host copy while the helper thread drains results
+            group_rows = max(1, (256 << 20) // (self.d * 4))
+            xd_group, g_lo, g_hi = None, 0, 0
+
+            def load_group(start_batch, row0):
+                rows, bj = 0, start_batch
+                while bj < len(batches) and (rows == 0 or rows + sizes[bj] <= group_rows):
+                    rows += sizes[bj]
+                    bj += 1
+                hx = self._pinned("xg", (rows, self.d), torch.float32)
+                r = 0
+                for b in batches[start_batch:bj]:
+                    b = np.ascontiguousarray(b, dtype=np.float32)
+                    if b.ndim != 2 or b.shape[1] != self.d:
+                        raise ValueError(f"query_embeds: expected (nq, {self.d}), got {b.shape}")
+                    hx[r:r + len(b)].copy_(torch.from_numpy(b))
+                    r += len(b)
+                compute.synchronize()                     # the pinned buffer is free (previous group consumed)
+                return hx.to(self.device, non_blocking=True), row0, row0 + rows
+
+            for bi, xb in enumerate(batches):
+                nb = sizes[bi]
+                if nb == 0:
+                    continue
+                slot = bi & 1
+                mark("begin")
+                if lo >= g_hi:
+                    xd_group, g_lo, g_hi = load_group(bi, lo)
+                mark("staged")
+                xd = xd_group[lo - g_lo: lo - g_lo + nb]
+                mark("h2d")
+                s, i = self.search_tensor(xd, k)
+                mark("search")
+                if ids_dev is not None:
+                    mapped = torch.empty_like(i)
+                    _lib.check(_lib.load().rc_map_ids(i.data_ptr(), ids_dev.data_ptr(), ids_dev.numel(), i.numel(),
+                                                      mapped.data_ptr(), ops._stream()), "rc_map_ids")
+                    i = mapped
+                done = torch.cuda.Event()
+                done.record(compute)
+                mark("mapped")
+                if busy[slot] is not None:                # the staging buffers of this slot are free again
+                    busy[slot].result()
+                mark("slotfree")
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(done)
+                    self._pinned(f"s{slot}", (nb, k), torch.float32).copy_(s, non_blocking=True)
+                    self._pinned(f"i{slot}", (nb, k), torch.int64).copy_(i, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(self._copy_stream)
+                busy[slot] = self._drain_pool.submit(drain, lo, lo + nb, slot, copied, (s, i))
+                lo += nb
+                mark("submitted")
+            for f in busy:
+                if f is not None:
+                    f.result()
+            mark("drained")
+        return out_s, out_i
+
+
 # ----------------------------------------------------------------------------------------------
 # Faiss index file (`faiss.write_index` / `read_index`) for IndexPQ: fourcc "IxPq"
 # (faiss/impl/index_write.cpp of the pinned 1.7.1: index header, ProductQuantizer, codes vector,

@@ -166,6 +166,14 @@ def test_reference_wrappers_and_mrr(oracle):
     assert np.array_equal(s, os_) and np.array_equal(ids, corpus_ids[oi])
     mrr = oracle.mrr_at_k(ids, corpus_ids[rel], 10)
     assert mrr == oracle.mrr_at_k(corpus_ids[oi], corpus_ids[rel], 10) and mrr > 0.3
+    # the pipelined multi-batch path (copy-back of batch i overlapping the scan of batch i+1) returns what the
+    # single-batch path and the generic per-batch loop (non-int64 ids) return
+    s1, ids1 = E.batch_search(qids, queries, corpus_ids, gpu, topk=10, batch_size=nq)
+    assert np.array_equal(s1, s) and np.array_equal(ids1, ids)
+    s3, ids3 = E.batch_search(qids, queries, corpus_ids.astype(np.int32), gpu, topk=10, batch_size=37)
+    assert np.array_equal(s3, s) and np.array_equal(ids3, ids)
+    s4, ids4 = E.batch_search(qids, queries, corpus_ids, gpu, topk=10, batch_size=37)
+    assert np.array_equal(s4, s) and np.array_equal(ids4, ids)
     # host-side IndexPQ.search (the --cpu_search call site) lands on the same kernels
     s2, i2 = index.search(queries[:5], 10)
     assert np.array_equal(i2, oi[:5])
