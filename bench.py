@@ -308,17 +308,32 @@ def main():
         as_launches = _lib.launch_count() - l0
         as_ms = max_over_ranks(e0.elapsed_time(e1))
         as_eps = Ksteps * ASSIGN_B * world / (as_ms / 1e3)
-        def assign_step_e2e(i):
-            x = xs_host[i].to(dev, non_blocking=True)             # H2D of the step's embeddings (pinned)
-            c_, mse_ = assign_step(x)
-            return c_.cpu(), float(mse_.detach())                 # D2H of the codes and the loss
+        # e2e: every step's embeddings come from pinned host memory and its codes + loss go back to the host;
+        # the H2D of step i+1 is issued on a copy stream while step i computes (double buffering)
+        copy_stream = torch.cuda.Stream(device=dev)
 
-        for i in range(W):                                        # e2e warm-up (allocator reaches steady state)
-            assign_step_e2e(i)
+        def fetch(i):
+            with torch.cuda.stream(copy_stream):
+                xd = xs_host[i].to(dev, non_blocking=True)        # H2D of the step's embeddings (pinned)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return xd, ev
+
+        def assign_e2e_loop(first, last):
+            nxt = fetch(first)
+            for i in range(first, last):
+                xd, ev = nxt
+                if i + 1 < last:
+                    nxt = fetch(i + 1)
+                torch.cuda.current_stream().wait_event(ev)
+                c_, mse_ = assign_step(xd)
+                res = c_.cpu(), float(mse_.detach())              # D2H of the codes and the loss
+            return res
+
+        assign_e2e_loop(0, W)                                     # e2e warm-up (allocator reaches steady state)
         barrier()
         t0 = time.perf_counter()
-        for i in range(W, W + Ksteps):
-            c_host, mse_host = assign_step_e2e(i)
+        c_host, mse_host = assign_e2e_loop(W, W + Ksteps)
         barrier()
         as_e2e = Ksteps * ASSIGN_B * world / max_over_ranks(time.perf_counter() - t0)
         # the dominant kernels: one Sinkhorn iteration = survivor-list pass (or re-selection) + reduce/update.

@@ -7,8 +7,8 @@
 //   table      (M, B, K) fp32, k fastest                     raw distances, centred IN PLACE by
 //                                                            rc_sinkhorn_begin (never widened to fp64)
 //   state      lu, lu_build, U (M,K) f64 | P (M,K) f64 (the all-reduce operand) | lv (M,B) f64 (dense pass) |
-//              partial (G,S,K) f64 | drift (M,2) f64 + decision | survivor lists: csr_ptr / csr_cnt (M,B) u32,
-//              pool_k u8 + pool_e f64 (64 entries per table row on average)
+//              partial (G,S,K) f64 | drift (M,2) f64 + decision | survivor records: row-pair directory (8 B per
+//              pair of rows) + pool of [32 x u16 lane header][E f64 x count] records (160 entries per row on average)
 //
 // Sinkhorn formulation.  The reference materialises Q = exp(-d~/eps) as (M,K,B) fp64 and divides it in place
 // 4x per iteration.  Here Q_t[k,b] = 2^(a + lu[k] + lv[b]), a = -d~ * log2(e)/eps, is never stored.
@@ -20,9 +20,11 @@
 //                fp64 sum.  A selection pass finds them (fp32 filter, ballot compaction), evaluates them in
 //                fp64 and emits them as per-row lists; list passes then iterate on the lists alone -- one
 //                multiplication per survivor -- until lu has drifted by more than the selection slack.
-//   Kernels: dist_table / nn_assign, sinkhorn_pass<BEGIN|STEP|FINISH> (dense), sinkhorn_step_sparse (selection),
-//            sinkhorn_step_csr (list), sinkhorn_update (row scaling, drift, U, decision), sinkhorn_reduce,
-//            sinkhorn_expand (Q for API parity).
+//   Kernels: dist_table / nn_assign (packed fp32), sinkhorn_pass<BEGIN|STEP|FINISH> (dense), sinkhorn_step_sparse
+//            (selection), sinkhorn_step_list (list), sinkhorn_reduce / sinkhorn_update / sinkhorn_reduce_update
+//            (row sums, row scaling, drift, U, decision), sinkhorn_finish_sparse (fp32-filtered argmax),
+//            sinkhorn_expand (Q for API parity).  Entry points: rc_sinkhorn_solve (one rank, one call) and
+//            rc_sinkhorn_begin / step / finish (ranks exchange the row sums between the calls).
 #include <math.h>
 #include <stdlib.h>
 
@@ -664,7 +666,7 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 // offset / count / fp32 maximum).  Between selections only lu changes: an element left out had
 // w - rowmax < -(MARGIN + SLACK) at selection time, and afterwards w - rowmax can grow by at most
 // spread = max_k(dlu) - min_k(dlu), dlu = lu - lu_build.  sinkhorn_update_kernel tracks that spread per
-// sub-vector; while max_m spread <= SK_SLACK the cheap pass (sinkhorn_step_csr_kernel) iterates on the
+// sub-vector; while max_m spread <= SK_SLACK the cheap pass (sinkhorn_step_list_kernel) iterates on the
 // lists alone -- no table read, no filter -- otherwise the selection pass runs again.  Both kernels are
 // launched every iteration and decide on the device (same inputs, same decision) which one works.
 // The dense kernel above remains the path for K != 256, for RC_SINKHORN_DENSE=1 and for the re-run

@@ -180,3 +180,34 @@ def test_shard_bounds_cover_exactly():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_warmup_host_helpers_match_the_oracle():
+    """The pure-torch pieces of the warm-up (empty-cluster split, Procrustes, seeded rotation, initial
+    centroids) run on CPU tensors too: same values as oracle/warmup_np.py."""
+    import numpy as np
+    import torch
+    from oracle import warmup_np as W
+    from repconc_b200 import warmup
+    r = np.random.default_rng(0)
+    c = r.standard_normal((3, 16, 6)).astype(np.float32)
+    counts = r.integers(1, 50, (3, 16))
+    counts[0, 4] = counts[0, 9] = counts[2, 0] = 0
+    counts[1, :] = 1                                   # nothing to split from: left alone
+    counts[1, 7] = 0
+    got = warmup.split_empty_clusters(torch.from_numpy(c), torch.from_numpy(counts.astype(np.int32))).numpy()
+    want = W.split_empty_clusters(c, counts)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[1], c[1])
+    x = r.standard_normal((500, 12)).astype(np.float32)
+    rec = (x @ np.linalg.qr(r.standard_normal((12, 12)))[0]).astype(np.float32)
+    A = warmup.procrustes(torch.from_numpy(x), torch.from_numpy(rec)).numpy()
+    np.testing.assert_allclose(A, W.procrustes(x, rec), atol=1e-5)
+    np.testing.assert_allclose(x @ A.T, rec, atol=1e-4)           # recovers the rotation that generated `rec`
+    R = warmup.random_rotation(24, 5, "cpu")
+    np.testing.assert_allclose((R @ R.t()).numpy(), np.eye(24), atol=1e-5)
+    assert torch.equal(R, warmup.random_rotation(24, 5, "cpu"))
+    c0 = warmup.initial_centroids(torch.from_numpy(x), 3, 16, seed=2)
+    assert c0.shape == (3, 16, 4)
+    rows = {tuple(np.round(v, 6)) for v in x.reshape(500, 3, 4)[:, 0, :]}
+    assert all(tuple(np.round(v, 6)) in rows for v in c0[0].numpy())     # centroids are training points

@@ -21,6 +21,19 @@ for (B, M, K, ds, T) in [(300, 4, 256, 16, 12), (70, 3, 64, 5, 4), (513, 2, 256,
     (mse + sur).backward()
     q = ops.decode(codes, c)
     q.sum().backward()
+# step-wise entry points, oversized survivor rows (list pass reading straight from the pool), warm-up kernels
+x = torch.randn((333, 4 * 16), generator=gen, device="cuda")
+c = torch.randn((4, 1, 16), generator=gen, device="cuda") + 1e-3 * torch.randn((4, 256, 16), generator=gen, device="cuda")
+k = ops.CudaAssignKernels(x, c)
+k.table(); k.begin(0.003)
+for _ in range(5):
+    k.step(0.003, 333)
+k.finish(0.003, True)
+k.table(); k.solve(0.003, 8, uint8=True)
+from repconc_b200 import warmup
+xw = torch.randn((2048, 32), generator=gen, device="cuda")
+cw, objs = warmup.train_pq(xw, 4, 256, niter=2, seed=1)
+warmup.code_histogram(ops.nn_assign(xw, cw), 256)
 M, ds = 16, 4
 c = torch.randn((M, 256, ds), generator=gen, device="cuda")
 for N, nq, k in [(3000, 9, 17), (300_000, 20, 100)]:
