@@ -445,10 +445,9 @@ template <int MT, bool SAMPLE = false>
 static int launch_cf_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
     auto kern = adc_scan_cf_kernel<MT, SAMPLE>;
     const size_t smem = (size_t)MT * ADC_K * 16;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     dim3 grid((unsigned)((a.nq + 7) / 8), (unsigned)splits);
     kern<<<grid, CF_THREADS, smem, st>>>(a);
@@ -534,10 +533,9 @@ template <int QP, int MT>
 static int launch_packed_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
     auto kern = adc_scan_packed_kernel<QP, MT>;
     const size_t smem = (size_t)a.M * ADC_K * 2 * QP;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     dim3 grid((unsigned)((a.nq + QP - 1) / QP), (unsigned)splits);
     kern<<<grid, SCAN_THREADS, smem, st>>>(a);
@@ -628,10 +626,9 @@ template <int QT, int MT>
 static int launch_scan_inst(const ScanArgs& a, int splits, cudaStream_t st) {
     auto kern = adc_scan_kernel<QT, MT>;
     const size_t smem = (size_t)a.M * ADC_K * 4 * QT;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     dim3 grid((unsigned)((a.nq + QT - 1) / QT), (unsigned)splits);
     kern<<<grid, SCAN_THREADS, smem, st>>>(a);
@@ -1053,12 +1050,11 @@ static int launch_lut(const float* queries, int64_t ldq, const float* c, int64_t
 }
 
 static int sort_smem_attr() {
-    static bool done = false;
-    if (!done) {
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
         RC_CUDA(cudaFuncSetAttribute(adc_rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
         RC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
-        done = true;
     }
     return RC_OK;
 }

@@ -1479,11 +1479,10 @@ static int launch_update(const SkState& s, int M, int K, double Bg, int check_ma
 // works (device-side decision from the drift the update kernel just wrote; force = 1: select).
 static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, int M, double eps, int force,
                               const SkState& s, int32_t* flags, cudaStream_t st, SkPart* ps_out, SkPart* pl_out) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM));
-        attr_done = true;
     }
     const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM), pl = sk_partition(B, M, LP_CTAS_PER_SM);
     const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;

@@ -55,6 +55,17 @@ inline int num_sms() {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// true the first time a call site runs on the current device: kernel function attributes (dynamic shared
+// memory opt-in) are per device, and one process may drive several (e.g. index replicas on every GPU)
+inline bool first_use_on_device(unsigned long long& seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 summation in the order of ATen's CPU sum kernel (inner contiguous reduction, 8-float
 // vectors, 4 independent accumulators, cascade of 4 levels).  The reference's distance table is
