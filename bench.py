@@ -381,7 +381,11 @@ def main():
                   "roofline": {"bound": "hbm", "kernel": "sinkhorn iteration (sinkhorn_step_list_kernel / "
                                                           "sinkhorn_step_sparse_kernel + sinkhorn_reduce_update_kernel)",
                                "achieved": alg_it / it_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": alg_it / it_s / 1e9 / hbm_peak, "traffic": None,
+                               "frac": alg_it / it_s / 1e9 / hbm_peak,
+                               # dram__bytes_read + dram__bytes_write of ONE sinkhorn_step_list_kernel launch at
+                               # this shape, from the committed `ncu --set full` capture
+                               # profiles/r01_sinkhorn_list_ncu.txt
+                               "traffic": 250.099968e6 + 4.836608e6,
                                "algorithmic_bytes_per_launch": alg_it, "launch_ms": it_s * 1e3,
                                "note": "algorithmic bytes = the fp32 table read once per half-iteration (SURVEY 8d); "
                                        "the iteration works on fp64 survivor lists (~190 MB per pass, ncu) and is "
