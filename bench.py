@@ -63,6 +63,8 @@ class ClockSampler:
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(self.__exit__)              # never leave the sampler behind if the bench dies
         except Exception:
             self.proc = None
         return self
@@ -72,7 +74,7 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.proc is not None and self.proc.poll() is None:
             time.sleep(0.25)
             self.proc.terminate()
             try:
@@ -222,15 +224,18 @@ def main():
     barrier()
     scan_ms, scan_launches = 0.0, 0
     l0 = _lib.launch_count()
-    with ClockSampler(local) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(W, W + Ksteps):
-            adc_step(i)
-            scan_ms += lib.rc_adc_last_scan_ms()
-            scan_launches += lib.rc_adc_last_scan_launches()
-        e1.record()
-        barrier()
+    # clocks / throttle reasons are sampled from here to the end of the last GPU-timed region (ADC, ADC e2e,
+    # assign, assign e2e): every sample is taken under load
+    clk = ClockSampler(local)
+    clk.__enter__()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + Ksteps):
+        adc_step(i)
+        scan_ms += lib.rc_adc_last_scan_ms()
+        scan_launches += lib.rc_adc_last_scan_launches()
+    e1.record()
+    barrier()
     adc_launches = _lib.launch_count() - l0
     adc_ms = max_over_ranks(e0.elapsed_time(e1))
     adc_qps = Ksteps * SEARCH_BATCH / (adc_ms / 1e3)
@@ -391,6 +396,8 @@ def main():
                                        "the iteration works on fp64 survivor lists (~190 MB per pass, ncu) and is "
                                        "bound by instruction issue, not HBM; launch_ms = mean over list and "
                                        "re-selection iterations incl. the reduce/update kernel"}}
+
+    clk.__exit__(None, None, None)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
     cpu_baseline = None
