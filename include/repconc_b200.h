@@ -35,7 +35,7 @@ extern "C" {
 #define RC_FLAG_NONFINITE 1 /* Q would hold NaN/Inf: models/repconc/modeling_repconc.py:64-65 */
 #define RC_FLAG_AMPLITUDE 2 /* `assert torch.all(amplitude > 0)` would fire: modeling_repconc.py:83 */
 #define RC_FLAG_BADCODE 4   /* rc_decode saw a code outside [0, K) */
-#define RC_FLAG_SPARSE_UNSAFE 8 /* a row kept < 2^-8/K of mass: re-run with rc_sinkhorn_set_dense(1) */
+#define RC_FLAG_SPARSE_UNSAFE 8 /* a row kept < 2^-8/K of mass or the survivor pool ran out: re-run with dense = 1 */
 #define RC_FLAG_PEER_TIMEOUT 16 /* rc_peer_allreduce_f64: a peer never signalled (bounded spin expired) */
 
 const char* rc_last_error(void);
@@ -94,11 +94,16 @@ int rc_dist_table(const float* x, int64_t ldx, const float* centroids, int64_t B
  * The all-reduces are the caller's (torch.distributed / NCCL on the same stream) -- the library
  * has no communicator.  iters == 0 is allowed (begin, finish).
  * ------------------------------------------------------------------------------------------- */
-/* Sinkhorn pass selection.  Default (0): for K == 256 the iteration passes evaluate only the table
- * elements within 2^-72 of their column sum (the rest cannot change an fp64 sum; bound in
- * csrc/assign.cu); 1: always the dense pass.  Env RC_SINKHORN_DENSE=1 sets the initial value.
- * Returns the previous setting. */
+/* Sinkhorn pass selection is PER CALL: the `dense` argument of rc_sinkhorn_step / finish / solve.
+ * dense = 0: for K == 256 the iteration passes evaluate only the table elements within 2^-72 of their
+ * column sum (the rest cannot change an fp64 sum; bound in csrc/assign.cu); dense = 1: always the dense
+ * pass (what the host re-runs with after RC_FLAG_SPARSE_UNSAFE).  rc_sinkhorn_set_dense only sets the
+ * process-wide default that is OR-ed with the argument (debugging / A-B runs; env RC_SINKHORN_DENSE=1
+ * sets its initial value); it returns the previous default. */
 int rc_sinkhorn_set_dense(int dense);
+/* test hook: usable survivor-pool capacity in entries per table row (0 = full allocation); returns the
+ * previous value.  Lets a test exhaust the pool -> RC_FLAG_SPARSE_UNSAFE on one rank only. */
+int64_t rc_sinkhorn_debug_pool_entries(int64_t entries_per_row);
 size_t rc_sinkhorn_state_bytes(int64_t B, int M, int K);
 /* device pointer to the (M,K) fp64 row-sum buffer inside `state` (the all-reduce operand) */
 double* rc_sinkhorn_rowsum_ptr(void* state, int64_t B, int M, int K);
@@ -107,7 +112,7 @@ int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M, int K
 /* step_index: 0 for the first step after rc_sinkhorn_begin, then 1, 2, ... (the first step always
  * runs the dense pass: its input columns are not normalised yet) */
 int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
-                     int step_index, void* state, int32_t* flags, void* stream);
+                     int step_index, int dense, void* state, int32_t* flags, void* stream);
 /* the transport plan itself, Q (M,K,B) fp64 with columns summing to 1 -- what the reference's
  * sinkhorn_algorithm returns (modeling_repconc.py:164-165); call instead of rc_sinkhorn_finish */
 int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
@@ -117,15 +122,18 @@ int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, i
  * normalisation fuse into one kernel per iteration because no all-reduce separates them).  This is
  * what RepCONC.quantize runs when torch.distributed is not initialised (modeling_repconc.py:61). */
 int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
-                      void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, void* stream);
+                      int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
+                      void* stream);
 /* diagnostics of the survivor lists the sparse pass currently holds (K == 256 only): out[0] = entries,
  * out[1] = longest row, out[2] = rows, out[3 + i] = rows with i*8 <= count < i*8+8 (i < 33). `out` is a
  * DEVICE array of 36 int64. */
 int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream);
-/* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0 */
+/* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0
+ * steps_done : number of rc_sinkhorn_step calls since rc_sinkhorn_begin (the last row sums get the sparse
+ *              pass's mass check only if they came from a step) */
 int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
-                       int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
-                       void* stream);
+                       int apply_rowsum, int steps_done, int dense, void* state, int64_t* codes_mb,
+                       uint8_t* codes_u8, int32_t* flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One-shot all-reduce (SUM, fp64, in place) of the row sums over NVLink peer memory: the

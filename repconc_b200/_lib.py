@@ -30,11 +30,13 @@ SIGNATURES = {
     "rc_sinkhorn_state_bytes": (c_size, [c_i64, c_int, c_int]),
     "rc_sinkhorn_rowsum_ptr": (c_ptr, [c_ptr, c_i64, c_int, c_int]),
     "rc_sinkhorn_begin": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_f64, c_ptr, c_ptr, c_ptr]),
-    "rc_sinkhorn_step": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_debug_pool_entries": (c_i64, [c_i64]),
+    "rc_sinkhorn_step": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "rc_sinkhorn_expand": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "rc_sinkhorn_finish": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
-                                   c_ptr]),
-    "rc_sinkhorn_solve": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_f64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_finish": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_f64, c_int, c_int, c_int, c_ptr, c_ptr,
+                                   c_ptr, c_ptr, c_ptr]),
+    "rc_sinkhorn_solve": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_f64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr]),
     "rc_sinkhorn_list_stats": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
     "rc_peer_allreduce_buffer_bytes": (c_size, [c_i64]),
     "rc_peer_allreduce_f64": (c_int, [c_ptr, c_int, c_int, c_i64, ctypes.c_uint32, c_ptr, c_ptr, c_ptr]),

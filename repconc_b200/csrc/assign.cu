@@ -375,6 +375,10 @@ static double sk_slack() {
     return v;
 }
 
+// test hook: usable survivor-pool capacity in entries per table row (0 = the allocation's SK_POOL_PER_ROW); lets a
+// test exhaust the pool on one rank only (rc_sinkhorn_debug_pool_entries)
+static int64_t g_pool_entries_override = 0;
+
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
     size_t off = 0;
     char* b = (char*)base;
@@ -413,6 +417,10 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
         s->pool = (unsigned char*)(b + o_pool);
         s->slack = sk_slack();
         s->pool_cap = pool;
+        if (g_pool_entries_override > 0) {
+            const uint64_t cap = (uint64_t)M * (uint64_t)B * sk_record_units((uint32_t)g_pool_entries_override);
+            if (cap < s->pool_cap) s->pool_cap = cap;
+        }
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
         s->lv = (double*)(b + o_lv);
@@ -1497,18 +1505,24 @@ static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, i
     return RC_OK;
 }
 
+// Process-wide DEFAULT of the pass selection (env RC_SINKHORN_DENSE / rc_sinkhorn_set_dense: debugging, A/B runs).
+// The choice that matters is per call: every entry point takes a `dense` argument, so a dense re-run on one
+// stream / thread never changes what another one executes.
 static int g_sinkhorn_dense = -1;  // -1: read RC_SINKHORN_DENSE from the environment on first use
-static bool sinkhorn_dense() {
+static bool sinkhorn_dense_default() {
     if (g_sinkhorn_dense < 0) {
         const char* e = getenv("RC_SINKHORN_DENSE");
         g_sinkhorn_dense = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
     return g_sinkhorn_dense == 1;
 }
+static bool sk_use_sparse(const void* table, int K, int dense) {
+    return K == SP_K && (((uintptr_t)table) & 15) == 0 && !dense && !sinkhorn_dense_default();
+}
 
 static int launch_finish(const float* table, int64_t B, int M, int K, double eps, const SkPart& p, const SkState& s,
-                         int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, cudaStream_t st) {
-    if (K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense()) {
+                         int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, int dense, cudaStream_t st) {
+    if (sk_use_sparse(table, K, dense)) {
         const SkPart pf = sk_partition(B, M, FS_CTAS_PER_SM);
         RC_CUDA(launch_chain(sinkhorn_finish_sparse_kernel, (unsigned)pf.G, (unsigned)SK_THREADS, 0, st, table, B, M,
                              RC_LOG2E / eps, pf, (const double*)s.lu, codes_mb, codes_u8, flags));
@@ -1524,8 +1538,14 @@ static int launch_finish(const float* table, int64_t B, int M, int K, double eps
 using namespace rc;
 
 RC_API int rc_sinkhorn_set_dense(int dense) {
-    const int old = sinkhorn_dense() ? 1 : 0;
+    const int old = sinkhorn_dense_default() ? 1 : 0;
     g_sinkhorn_dense = dense ? 1 : 0;
+    return old;
+}
+
+RC_API int64_t rc_sinkhorn_debug_pool_entries(int64_t entries_per_row) {
+    const int64_t old = g_pool_entries_override;
+    g_pool_entries_override = entries_per_row;
     return old;
 }
 
@@ -1647,7 +1667,8 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
  * (sinkhorn_reduce_update_kernel); everything else is the kernels of the step-wise entry points in the same
  * order, so the results are bit-identical to the step-wise sequence with B_global == B. */
 RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
-                             void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags, void* stream) {
+                             int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
+                             void* stream) {
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(minmax, "rc_sinkhorn_solve: null minmax");
@@ -1668,14 +1689,14 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
         if (codes_u8) RC_CUDA(cudaMemsetAsync(codes_u8, 0, (size_t)M * B, st));
         return RC_OK;
     }
-    const bool sparse = K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
+    const bool sparse = sk_use_sparse(table, K, dense);
     // which pass wrote the partials the next reduce+update consumes
     int csr_mode = 0, force = 0;
     SkPart pin = p, plist = p;
     for (int it = 0; it < iters; ++it) {
         const bool last = it == iters - 1;
         RC_CUDA(launch_chain(sinkhorn_reduce_update_kernel, (unsigned)M, 256u, 0, st, s.partial, pin, plist, K, csr_mode,
-                             M, force, (!last && sparse && it > 0) ? 1 : 0, s, flags));
+                             M, force, (sparse && it > 0) ? 1 : 0, s, flags));
         RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
         if (last) break;
         if (sparse) {
@@ -1688,11 +1709,11 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
             if (rc) return rc;
         }
     }
-    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
+    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, dense, st);
 }
 
 RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
-                            int step_index, void* state, int32_t* flags, void* stream) {
+                            int step_index, int dense, void* state, int32_t* flags, void* stream) {
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(B_global >= B, "rc_sinkhorn_step: B_global < B");
@@ -1703,7 +1724,7 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
     // The sparse pass needs rows (centroids) that kept their share of the mass through the previous column
     // normalisation; the update kernel checks that from the second STEP on (the first update sees the row
     // sums of the unnormalised Q0, which say nothing about it).
-    const bool sparse = K == SP_K && (((uintptr_t)table) & 15) == 0 && !sinkhorn_dense();
+    const bool sparse = sk_use_sparse(table, K, dense);
     rc = launch_update(s, M, K, (double)B_global, (sparse && step_index > 0) ? 1 : 0, flags, st);
     if (rc) return rc;
     if (sparse) {
@@ -1753,8 +1774,8 @@ RC_API int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, i
 }
 
 RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
-                              int apply_rowsum, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
-                              void* stream) {
+                              int apply_rowsum, int steps_done, int dense, void* state, int64_t* codes_mb,
+                              uint8_t* codes_u8, int32_t* flags, void* stream) {
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(codes_mb || codes_u8, "rc_sinkhorn_finish: no output");
@@ -1771,8 +1792,11 @@ RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, i
         return RC_OK;
     }
     if (apply_rowsum) {
-        rc = launch_update(s, M, K, (double)B_global, 0, flags, st);
+        // the row sums of the last sparse pass get the same mass check as every other one (steps_done >= 1: they
+        // come from a STEP pass, not from BEGIN's unnormalised Q0 -- see rc_sinkhorn_step)
+        const int check = (sk_use_sparse(table, K, dense) && steps_done >= 1) ? 1 : 0;
+        rc = launch_update(s, M, K, (double)B_global, check, flags, st);
         if (rc) return rc;
     }
-    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, st);
+    return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, dense, st);
 }

@@ -151,6 +151,11 @@ def sinkhorn_algorithm(out: Tensor, epsilon: float, sinkhorn_iterations: int, us
     """modeling_repconc.py:137-165 as a function: `out` (M, K, B) = -centred distances (values in
     [-1, 1], fp64 or fp32); returns Q (M, K, B) fp64 with columns summing to 1.
 
+    Contract on `out`: the kernels iterate on an fp32 table, so `out` is cast to fp32.  That is EXACT for what
+    RepCONC.quantize passes (`-center_distance_for_constraint(...)`: fp32 values widened by `.double()`, :54-56)
+    and for any fp32 input; an fp64 `out` carrying more than 24 significant bits is rounded to fp32 first,
+    i.e. the result is the reference's for `out.float().double()`.
+
     The training path (RepCONC.quantize) never materialises Q; this entry point exists for callers
     that want the transport plan itself.  It runs the same kernels on the (M,B,K) fp32 table rebuilt
     from `out` and expands Q from the row scaling with rc_sinkhorn_expand."""
@@ -170,31 +175,34 @@ def sinkhorn_algorithm(out: Tensor, epsilon: float, sinkhorn_iterations: int, us
         off = lib.rc_sinkhorn_rowsum_ptr(base, B, M, K) - base
         P = state[off: off + M * K * 8].view(torch.float64).view(M, K)
         Q = torch.empty((M, K, B), dtype=torch.float64, device=out.device)
-        dense_prev = None
-        try:
-            while True:
-                # the kernels consume the (M,B,K) fp32 centred table; `out` is its negated transpose
-                table = (-out).transpose(1, 2).float().contiguous()
-                flags = torch.zeros(1, dtype=torch.int32, device=out.device)
-                ops._lib.check(lib.rc_sinkhorn_begin(table.data_ptr(), minmax.data_ptr(), B, M, K, float(epsilon),
-                                                     base, flags.data_ptr(), sp), "rc_sinkhorn_begin")
-                for it in range(max(sinkhorn_iterations - 1, 0)):
-                    if use_distrib_train:
-                        dist.all_reduce(P)
-                    ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), it,
-                                                        base, flags.data_ptr(), sp), "rc_sinkhorn_step")
-                if use_distrib_train and sinkhorn_iterations >= 1:
+        if sinkhorn_iterations <= 0:
+            # no iteration: the reference returns exp(out/eps) / sum(Q) * B, whose columns are NOT normalised
+            # (:141-152,164).  Not on any training path; three plain torch ops in fp64 keep the exact values.
+            Q = torch.exp(out.double() / epsilon)
+            sum_Q = Q.sum(-1, keepdim=True).sum(-2, keepdim=True)
+            if use_distrib_train:
+                dist.all_reduce(sum_Q)
+            Q /= sum_Q
+            Q *= B * world
+            return Q
+        for dense in (0, 1):
+            # the kernels consume the (M,B,K) fp32 centred table; `out` is its negated transpose
+            table = (-out).transpose(1, 2).float().contiguous()
+            flags = torch.zeros(1, dtype=torch.int32, device=out.device)
+            ops._lib.check(lib.rc_sinkhorn_begin(table.data_ptr(), minmax.data_ptr(), B, M, K, float(epsilon),
+                                                 base, flags.data_ptr(), sp), "rc_sinkhorn_begin")
+            for it in range(sinkhorn_iterations - 1):
+                if use_distrib_train:
                     dist.all_reduce(P)
-                ops._lib.check(lib.rc_sinkhorn_expand(table.data_ptr(), B, B * world, M, K, float(epsilon),
-                                                      1 if sinkhorn_iterations >= 1 else 0, base, Q.data_ptr(),
-                                                      flags.data_ptr(), sp), "rc_sinkhorn_expand")
-                if int(flags.item()) & ops.FLAG_SPARSE_UNSAFE and dense_prev is None:
-                    dense_prev = lib.rc_sinkhorn_set_dense(1)     # redo with the dense pass
-                    continue
-                break
-        finally:
-            if dense_prev is not None:
-                lib.rc_sinkhorn_set_dense(dense_prev)
+                ops._lib.check(lib.rc_sinkhorn_step(table.data_ptr(), B, B * world, M, K, float(epsilon), it,
+                                                    dense, base, flags.data_ptr(), sp), "rc_sinkhorn_step")
+            if use_distrib_train:
+                dist.all_reduce(P)
+            ops._lib.check(lib.rc_sinkhorn_expand(table.data_ptr(), B, B * world, M, K, float(epsilon), 1, base,
+                                                  Q.data_ptr(), flags.data_ptr(), sp), "rc_sinkhorn_expand")
+            fl = ops.reduce_flags(flags, use_distrib_train)
+            if not (fl & ops.FLAG_SPARSE_UNSAFE):
+                break                                     # otherwise: once more with the dense pass, on every rank
     return Q
 
 

@@ -19,6 +19,7 @@ FLAG_AMPLITUDE = 2
 FLAG_BADCODE = 4
 FLAG_SPARSE_UNSAFE = 8
 FLAG_PEER_TIMEOUT = 16
+N_FLAG_BITS = 5
 
 
 def _stream():
@@ -138,7 +139,7 @@ class CudaAssignKernels:
         self.P = self.state[off: off + self.M * self.K * 8].view(torch.float64).view(self.M, self.K)
         self.nsteps = 0
 
-    def solve(self, eps, iters, uint8=False):
+    def solve(self, eps, iters, uint8=False, dense=False):
         """single-rank Sinkhorn + argmax in one library call (rc_sinkhorn_solve); needs table() first"""
         self._alloc_state()
         if uint8:
@@ -148,8 +149,8 @@ class CudaAssignKernels:
             out = torch.empty((self.M, self.B), dtype=torch.int64, device=self.device)
             mb, u8 = out.data_ptr(), None
         _lib.check(self.lib.rc_sinkhorn_solve(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, self.M, self.K,
-                                              float(eps), int(iters), self.state.data_ptr(), mb, u8,
-                                              self.flags.data_ptr(), _stream()), "rc_sinkhorn_solve")
+                                              float(eps), int(iters), 1 if dense else 0, self.state.data_ptr(), mb,
+                                              u8, self.flags.data_ptr(), _stream()), "rc_sinkhorn_solve")
         return out if uint8 else out.t()
 
     def begin(self, eps):
@@ -159,14 +160,15 @@ class CudaAssignKernels:
                    "rc_sinkhorn_begin")
         return self.P
 
-    def step(self, eps, B_global):
+    def step(self, eps, B_global, dense=False):
         _lib.check(self.lib.rc_sinkhorn_step(self.tab.data_ptr(), self.B, int(B_global), self.M, self.K, float(eps),
-                                             self.nsteps, self.state.data_ptr(), self.flags.data_ptr(), _stream()),
+                                             self.nsteps, 1 if dense else 0, self.state.data_ptr(),
+                                             self.flags.data_ptr(), _stream()),
                    "rc_sinkhorn_step")
         self.nsteps += 1
         return self.P
 
-    def finish(self, eps, apply_rowsum, uint8=False, B_global=None):
+    def finish(self, eps, apply_rowsum, uint8=False, B_global=None, dense=False):
         if uint8:
             out = torch.empty((self.B, self.M), dtype=torch.uint8, device=self.device)
             mb, u8 = None, out.data_ptr()
@@ -175,27 +177,49 @@ class CudaAssignKernels:
             mb, u8 = out.data_ptr(), None
         _lib.check(self.lib.rc_sinkhorn_finish(self.tab.data_ptr(), self.B,
                                                int(B_global) if B_global is not None else self.B, self.M,
-                                               self.K, float(eps), 1 if apply_rowsum else 0, self.state.data_ptr(), mb, u8,
+                                               self.K, float(eps), 1 if apply_rowsum else 0, self.nsteps,
+                                               1 if dense else 0, self.state.data_ptr(), mb, u8,
                                                self.flags.data_ptr(), _stream()), "rc_sinkhorn_finish")
         return out if uint8 else out.t()
 
     def read_flags(self):
         return int(self.flags.item())
 
+    def clear_flags(self):
+        self.flags.zero_()
+
     def set_dense(self, dense):
-        """select the dense Sinkhorn pass (True) or the default sparse one; returns the previous setting"""
+        """process-wide DEFAULT of the pass selection (tests / A-B runs); the product passes `dense` per call.
+        Returns the previous default."""
         return bool(self.lib.rc_sinkhorn_set_dense(1 if dense else 0))
 
 
-def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=False, _retry_dense=False):
+def reduce_flags(flags, distributed, group=None):
+    """The flag word of an assignment as EVERY rank must see it: the bits are OR-ed over the ranks (a bit such as
+    SPARSE_UNSAFE can be raised from rank-local data -- pool exhaustion -- and the ranks must take the same
+    decision or their collective sequences diverge).  `flags`: int32[1] tensor, or an int (emulated kernels)."""
+    if not distributed:
+        return int(flags.item()) if isinstance(flags, torch.Tensor) else int(flags)
+    if isinstance(flags, torch.Tensor):
+        bits = ((flags.reshape(1) >> torch.arange(N_FLAG_BITS, device=flags.device)) & 1).to(torch.int32)
+    else:
+        bits = torch.tensor([(int(flags) >> i) & 1 for i in range(N_FLAG_BITS)], dtype=torch.int32)
+    dist.all_reduce(bits, dist.ReduceOp.MAX, group=group)      # OR, bit by bit (NCCL has no BOR)
+    return sum(int(b) << i for i, b in enumerate(bits.tolist()))
+
+
+def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=False, dense=False):
     """Host sequence of RepCONC.quantize with use_constraint=True (modeling_repconc.py:53-66):
     which kernel runs when, and where the reference's three all-reduces go
       * MAX / MIN of the per-sub-vector extrema       (:78-80)
       * SUM of the row sums, once per iteration       (:157; the total-sum all-reduce of :151 cancels
         in the first row normalisation and is not needed)
       * B *= world_size                               (:150)
-    `kern` provides table/begin/step/finish/read_flags (CudaAssignKernels in the product)."""
+    `kern` provides table/begin/step/finish/read_flags (CudaAssignKernels in the product).
+    `dense`: run the dense Sinkhorn pass (the re-run after RC_FLAG_SPARSE_UNSAFE); it is an argument of every
+    kernel call, not process state."""
     world = dist.get_world_size(group) if distributed else 1
+    iters = max(int(iters), 0)
     minmax = kern.table()
     if distributed:
         # one collective for both extrema: MAX over [max, -min]
@@ -204,8 +228,13 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
         minmax[1].neg_()
     B_global = kern.B * world
     if not distributed and hasattr(kern, "solve") and not _stepwise():
-        codes = kern.solve(eps, max(int(iters), 0), uint8=uint8)
-        return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense)
+        codes = kern.solve(eps, iters, uint8=uint8, dense=dense)
+        return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, dense)
+    if distributed and hasattr(kern, "solve_fused") and not _stepwise():
+        # W ranks, one persistent kernel per rank: the row sums are exchanged over NVLink peer memory inside it
+        codes = kern.solve_fused(eps, iters, B_global, group, uint8=uint8, dense=dense)
+        if codes is not None:
+            return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, dense)
     P = kern.begin(eps)
     # row-sum exchange: one-shot NVLink peer-memory all-reduce when available, NCCL otherwise
     reducer = None
@@ -219,35 +248,35 @@ def constrained_assign_driver(kern, eps, iters, distributed, group=None, uint8=F
         else:
             dist.all_reduce(P, dist.ReduceOp.SUM, group=group)
 
-    for _ in range(max(int(iters) - 1, 0)):
+    for _ in range(max(iters - 1, 0)):
         if distributed:
             sum_rows(P)
-        P = kern.step(eps, B_global)
+        P = kern.step(eps, B_global, dense=dense)
     if distributed and iters >= 1:
         sum_rows(P)
-    codes = kern.finish(eps, iters >= 1, uint8=uint8, B_global=B_global)
-    return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense)
+    codes = kern.finish(eps, iters >= 1, uint8=uint8, B_global=B_global, dense=dense)
+    return _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, dense)
 
 
 def _stepwise():
-    """RC_SINKHORN_STEPWISE=1: single-rank assignments also go through begin/step/finish (tests, debugging)"""
+    """RC_SINKHORN_STEPWISE=1: assignments go through begin/step/finish with the row sums exchanged between the
+    calls, instead of the single persistent kernel (tests, debugging)"""
     import os
     return os.environ.get("RC_SINKHORN_STEPWISE", "0") not in ("", "0")
 
 
-def _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, _retry_dense):
-    flags = kern.read_flags()
-    if flags & FLAG_SPARSE_UNSAFE and not _retry_dense:
-        # the sparse pass's error bound did not hold for this input (a centroid kept < 2^-12/K of mass):
-        # redo the whole assignment with the dense pass.  Every rank sees the same all-reduced row sums,
-        # so every rank takes this branch together.
-        prev = kern.set_dense(True)
-        try:
-            return constrained_assign_driver(kern, eps, iters, distributed, group, uint8, _retry_dense=True)
-        finally:
-            kern.set_dense(prev)
+def _check_assign_flags(kern, codes, eps, iters, distributed, group, uint8, dense):
+    flags = reduce_flags(kern.flags if hasattr(kern, "flags") else kern.read_flags(), distributed, group)
     if flags & FLAG_PEER_TIMEOUT:
-        raise _lib.RepconcLibraryError("peer all-reduce timed out: a rank never reached the exchange")
+        raise _lib.RepconcLibraryError("peer all-reduce timed out: a rank never reached the exchange "
+                                       "(RC_PEER_TIMEOUT_MS bounds the wait)")
+    if flags & FLAG_SPARSE_UNSAFE and not dense:
+        # the sparse pass's error bound did not hold for this input (a centroid kept < 2^-8/K of the mass, or the
+        # survivor pool ran out -- the latter depends on the rank's own rows): redo the whole assignment with
+        # the dense pass.  `flags` is OR-ed over the ranks, so every rank takes this branch together.
+        if hasattr(kern, "clear_flags"):
+            kern.clear_flags()
+        return constrained_assign_driver(kern, eps, iters, distributed, group, uint8, dense=True)
     if flags & FLAG_AMPLITUDE:
         raise AssertionError("amplitude > 0 (center_distance_for_constraint)")
     if flags & FLAG_NONFINITE:

@@ -24,6 +24,13 @@ ASSIGN_CASES = {
     "m64_b256":    dict(D=768, M=64, K=256, B=256,  eps=0.003, iters=100, seed=20, centroids="randn"),
     "b1":          dict(D=128, M=8,  K=256, B=1,    eps=0.003, iters=5,   seed=21, centroids="randn"),
 }
+# BASELINE-size batches (configs[2] and the per-rank slab of configs[4]): the reference needs ~20-60 s and
+# 13-26 GB for each in the build container; only codes, extrema, table hashes and the top-1/top-2 gap (fp16)
+# are stored
+ASSIGN_BIG_CASES = {
+    "m48_b8192":   dict(D=768, M=48, K=256, B=8192, eps=0.003, iters=50, seed=61, centroids="randn"),
+    "m96_b8192":   dict(D=768, M=96, K=256, B=8192, eps=0.003, iters=50, seed=62, centroids="randn"),
+}
 # two-rank run of the reference itself (gloo): each rank holds B/2 rows
 DIST_CASES = {
     "dist2_ds16":  dict(D=128, M=8, K=256, B=512, eps=0.003, iters=50, seed=31, centroids="randn", world=2),

@@ -30,6 +30,9 @@ class EmulatedAssignKernels:
         self.x, self.c = x, c
         self.M, self.K, self.ds = c.shape
         self.B = x.shape[0]
+        self.calls = []
+        self._flags = 0
+        self.unsafe_on_sparse = False             # test hook: this rank's sparse pass reports pool exhaustion
 
     def table(self):
         self.tab = self.O.dist_table(self.x, self.c)                     # (M,B,K) fp32
@@ -49,7 +52,8 @@ class EmulatedAssignKernels:
     def _update(self):
         self.lu = self.lu - np.log(self.K * self.P.numpy())
 
-    def step(self, eps, B_global):
+    def step(self, eps, B_global, dense=False):
+        self.calls.append(("step", bool(dense)))
         self._update()
         w = self.a + self.lu[:, None, :] + self.lv[:, :, None]
         q = np.exp(w)
@@ -58,7 +62,10 @@ class EmulatedAssignKernels:
         self.P = torch.from_numpy((q / z[:, :, None]).sum(1))
         return self.P
 
-    def finish(self, eps, apply_rowsum, uint8=False, B_global=None):
+    def finish(self, eps, apply_rowsum, uint8=False, B_global=None, dense=False):
+        self.calls.append(("finish", bool(dense)))
+        if not dense and self.unsafe_on_sparse:
+            self._flags |= 8                      # RC_FLAG_SPARSE_UNSAFE raised from this rank's own data
         if apply_rowsum and B_global == 1:          # single column: exact tie in the reference -> code 0
             return torch.zeros((self.B, self.M), dtype=torch.int64)
         if apply_rowsum:
@@ -67,10 +74,10 @@ class EmulatedAssignKernels:
         return torch.from_numpy(np.argmax(w, axis=2).T.copy())
 
     def read_flags(self):
-        return 0
+        return self._flags
 
-    def set_dense(self, dense):
-        return False
+    def clear_flags(self):
+        self._flags = 0
 
 
 def _worker(rank, world, port, case, ret):
@@ -95,6 +102,37 @@ def test_driver_two_ranks_gloo_matches_reference_two_ranks():
         mp.spawn(_worker, args=(2, 29733, case, ret), nprocs=2, join=True)
         codes = np.concatenate([ret[0], ret[1]], 0)
     assert np.array_equal(codes, g["codes_conc"].astype(np.int64))
+
+
+def _asym_worker(rank, world, port, case, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from repconc_b200.ops import constrained_assign_driver
+    x, c = GC.assign_inputs(case)
+    per = case["B"] // world
+    kern = EmulatedAssignKernels(x[rank * per:(rank + 1) * per], c)
+    kern.unsafe_on_sparse = rank == 1            # ONLY rank 1 sees RC_FLAG_SPARSE_UNSAFE
+    codes = constrained_assign_driver(kern, case["eps"], case["iters"], distributed=True)
+    ret[rank] = (codes.numpy(), kern.calls)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_local_sparse_unsafe_flag_reruns_densely_on_every_rank():
+    """RC_FLAG_SPARSE_UNSAFE raised on ONE rank only (survivor-pool exhaustion depends on the rank's own rows):
+    the flag word is OR-ed over the ranks, so both ranks redo the assignment with the dense pass in lock step
+    (a rank re-entering the collective sequence alone would hang) and the codes are the reference's."""
+    case = GC.DIST_CASES["dist2_ds16"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "assign_dist2_ds16.npz"))
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_asym_worker, args=(2, 29735, case, ret), nprocs=2, join=True)
+        (c0, calls0), (c1, calls1) = ret[0], ret[1]
+    assert np.array_equal(np.concatenate([c0, c1], 0), g["codes_conc"].astype(np.int64))
+    assert calls0 == calls1                                     # identical kernel / collective sequence
+    n = case["iters"]
+    assert calls0 == [("step", False)] * (n - 1) + [("finish", False)] + [("step", True)] * (n - 1) + [("finish", True)]
 
 
 def test_driver_single_rank_matches_golden():

@@ -112,6 +112,60 @@ def test_filtered_scan_path_large_corpus(oracle):
     assert np.array_equal(i10, oi[:, :10]) and np.array_equal(s10, os_[:, :10])
 
 
+@pytest.mark.parametrize("M,ds,N", [(32, 24, 300_000), (64, 12, 280_000), (96, 8, 270_000), (48, 16, 330_000),
+                                    (40, 4, 300_000), (12, 8, 300_000), (56, 4, 290_001)])
+def test_filtered_scan_every_kernel_family_vs_oracle(oracle, M, ds, N):
+    """Above the dense-path limit (262,144 docs) every M takes sampled thresholds + a packed integer filter scan +
+    exact re-score: the conflict-free kernel (M % 8 == 0), the 4-query / 2-query variants for wide codes
+    (M = 64, 96: the reference's other canonical settings) and the thread-per-document gather (other M).
+    Scores and ids must equal the oracle's bit for bit, for k = 10 and k = 1000."""
+    r = np.random.default_rng(1000 + M)
+    nq = 19
+    c = r.standard_normal((M, 256, ds), dtype=np.float32)
+    codes = r.integers(0, 256, size=(N, M), dtype=np.uint8)
+    codes[N // 3: N // 3 + 40] = codes[11]                     # exact ties across the corpus
+    q = r.standard_normal((nq, M * ds), dtype=np.float32)
+    q[3] = 0.0                                                 # constant table: every document ties
+    idx = _index(c, codes)
+    for k in (1000, 10):
+        s, i = idx.search(q, k)
+        assert idx.last_stats["sample"] > 0
+        os_, oi = oracle.adc_search(q, c, codes, k)
+        assert np.array_equal(s, os_) and np.array_equal(i, oi), (M, k)
+    assert idx.last_stats["filtered"] >= nq - 1
+
+
+def test_full_size_queries_vs_oracle(oracle):
+    """BASELINE configs[1] corpus size (8,841,823 docs, M=48, k=1000) generated by the section-8(d) recipe in
+    miniature (codes = NN assign of synthetic documents by the path itself, queries = document + 0.5 noise):
+    16 queries against the oracle's exhaustive scan, bit for bit, and identical MRR@10."""
+    from repconc_b200 import ops
+    from repconc_b200.faiss_compat import GpuIndexPQ
+    N, M, ds, nq, k = 8_841_823, 48, 16, 16, 1000
+    D = M * ds
+    gen = torch.Generator(device="cuda").manual_seed(4242)
+    seed_docs = torch.randn((256, D), generator=gen, device="cuda")
+    c = seed_docs.reshape(256, M, ds).transpose(0, 1).contiguous()          # trained-like centroids
+    codes = torch.empty((N, M), dtype=torch.uint8, device="cuda")
+    rel = torch.randint(0, N, (nq,), generator=gen, device="cuda")
+    qs = torch.empty((nq, D), device="cuda")
+    blk = 1 << 18
+    for lo in range(0, N, blk):
+        hi = min(N, lo + blk)
+        docs = torch.randn((hi - lo, D), generator=gen, device="cuda")
+        codes[lo:hi] = ops.nn_assign(docs, c, uint8=True)
+        sel = ((rel >= lo) & (rel < hi)).nonzero().flatten()
+        if len(sel):
+            qs[sel] = docs[rel[sel] - lo]
+    qs += 0.5 * torch.randn((nq, D), generator=gen, device="cuda")
+    idx = GpuIndexPQ(codes, c)
+    s, i = idx.search_tensor(qs, k)
+    os_, oi = oracle.adc_search(qs.cpu().numpy(), c.cpu().numpy(), codes.cpu().numpy(), k)
+    assert np.array_equal(s.cpu().numpy(), os_) and np.array_equal(i.cpu().numpy(), oi)
+    relh = rel.cpu().numpy()
+    assert oracle.mrr_at_k(i.cpu().numpy(), relh, 10) == oracle.mrr_at_k(oi, relh, 10)
+
+
 def test_fallback_when_thresholds_fail(oracle):
     """Adversarial corpus for the sampler: every high scorer sits outside the sampled blocks, or a
     huge tie group overflows the candidate list -> those queries must take the exact fallback."""

@@ -64,6 +64,63 @@ def test_constrained_assign_codes_bit_exact(name, oracle):
     assert np.array_equal(got, oracle.constrained_assign(x, c, case["eps"], case["iters"])["codes"])
 
 
+@pytest.mark.parametrize("name", list(GC.ASSIGN_BIG_CASES))
+def test_baseline_batch_bit_exact_vs_reference(name):
+    """BASELINE-size batches (8192 x 768; M=48 = configs[2], M=96 = the per-rank slab of configs[4], T=50) against
+    fixtures produced by the imported reference: fp32 table and centred table by sha256, extrema, NN codes and the
+    constrained codes, bit for bit.  The sparse passes' behaviour (re-selections, pool use, drift) depends on B, so
+    this is the size that has to be pinned."""
+    from repconc_b200 import ops
+    from repconc_b200.modeling_repconc import RepCONC
+    case = GC.ASSIGN_BIG_CASES[name]
+    g = golden("assign_" + name)
+    x, c = GC.assign_inputs(case)
+    assert GC.digest(x, c) == str(g["input_sha"])
+    xd, cd = _dev(x), _dev(c)
+    table, minmax, flags = ops.dist_table(xd, cd)
+    assert GC.digest(table.cpu().numpy()) == str(g["table_sha"])
+    assert np.array_equal(minmax[0].cpu().numpy(), g["max"]) and np.array_equal(minmax[1].cpu().numpy(), g["min"])
+    centred = RepCONC.center_distance_for_constraint(table)
+    assert GC.digest(centred.cpu().numpy()) == str(g["centred_sha"])
+    del table, centred
+    assert np.array_equal(ops.nn_assign(xd, cd, uint8=True).cpu().numpy(), g["codes_nn"])
+    for stepwise in (False, True):          # the persistent solve and the begin/step/finish sequence
+        if stepwise:
+            kern = ops.CudaAssignKernels(xd, cd)
+            kern.table()
+            kern.begin(case["eps"])
+            for _ in range(case["iters"] - 1):
+                kern.step(case["eps"], case["B"])
+            got = kern.finish(case["eps"], True).cpu().numpy()
+            assert kern.read_flags() == 0
+        else:
+            got = ops.constrained_assign(xd, cd, case["eps"], case["iters"], distributed=False).cpu().numpy()
+        want = g["codes_conc"].astype(np.int64)
+        bad = np.argwhere(got != want)
+        msg = "; ".join(f"(b={b},m={m}) gap={float(g['top2_gap'][b, m]):.3e}" for b, m in bad[:8])
+        assert len(bad) == 0, f"{len(bad)} code mismatches vs reference (stepwise={stepwise}): {msg}"
+
+
+def test_pool_exhaustion_flags_and_reruns_densely():
+    """Survivor-pool exhaustion (rank-local data decides it) raises RC_FLAG_SPARSE_UNSAFE and the driver redoes the
+    assignment with the dense pass: same codes as the reference."""
+    from repconc_b200 import ops, _lib
+    lib = _lib.load()
+    case = GC.ASSIGN_CASES["m48_b1024"]
+    g = golden("assign_m48_b1024")
+    x, c = GC.assign_inputs(case)
+    prev = lib.rc_sinkhorn_debug_pool_entries(1)
+    try:
+        kern = ops.CudaAssignKernels(_dev(x), _dev(c))
+        kern.table()
+        kern.solve(case["eps"], case["iters"])
+        assert kern.read_flags() & ops.FLAG_SPARSE_UNSAFE
+        got = ops.constrained_assign(_dev(x), _dev(c), case["eps"], case["iters"], distributed=False)
+    finally:
+        lib.rc_sinkhorn_debug_pool_entries(prev)
+    assert np.array_equal(got.cpu().numpy(), g["codes_conc"].astype(np.int64))
+
+
 def test_constrained_assign_uint8_and_strided_input():
     from repconc_b200 import ops
     case = GC.ASSIGN_CASES["ds16_b512"]

@@ -85,6 +85,51 @@ def run_assign(name, case):
           f"nn!=conc {np.mean(codes_nn != codes_conc):.3f}")
 
 
+def run_assign_big(name, case):
+    """BASELINE-size batch: codes (constraint on / off), extrema, table hashes, top-1/top-2 gap of Q."""
+    import gc
+    import time
+    from repconc.models.repconc.modeling_repconc import RepCONC, sinkhorn_algorithm
+    x, c = GC.assign_inputs(case)
+    D, M, K, B = case["D"], case["M"], case["K"], case["B"]
+    model = make_ref_model(D, M, K, c, True, case["eps"], case["iters"])
+    xt = torch.from_numpy(x)
+    t0 = time.perf_counter()
+    codes_conc = model.quantize(xt).contiguous().numpy()
+    t_ref = time.perf_counter() - t0
+    model.use_constraint = False
+    codes_nn = model.quantize(xt).contiguous().numpy()
+    gc.collect()
+    with torch.no_grad():
+        # the table sub-vector by sub-vector (same broadcast-sub / pow / sum ATen kernels, without the 13 GB temp)
+        table = torch.empty((M, B, K))
+        xm = xt.reshape(B, M, 1, -1).transpose(0, 1)
+        for m in range(M):
+            table[m] = ((xm[m:m + 1] - model.centroids[m:m + 1].unsqueeze(1)) ** 2).sum(-1)[0]
+        mx = table.max(-1).values.max(-1).values
+        mn = table.min(-1).values.min(-1).values
+        tsha = sha_table(table.numpy())
+        centred = RepCONC.center_distance_for_constraint(table)
+        del table
+        csha = sha_table(centred.numpy())
+        Q = sinkhorn_algorithm(-centred.double().transpose(1, 2), case["eps"], case["iters"], False)
+        del centred
+        Qt = Q.transpose(1, 2)  # M,B,K
+        top2 = torch.topk(Qt, 2, dim=-1).values
+        gap = ((top2[..., 0] - top2[..., 1]) / top2[..., 0]).t().contiguous().numpy().astype(np.float16)
+        assert np.array_equal(torch.argmax(Qt, -1).t().numpy(), codes_conc)
+        q_rowsum = Q.sum(2).numpy()
+    np.savez_compressed(
+        os.path.join(OUT, f"assign_{name}.npz"),
+        input_sha=GC.digest(x, c), codes_conc=codes_conc.astype(np.uint8), codes_nn=codes_nn.astype(np.uint8),
+        table_sha=tsha, centred_sha=csha, max=mx.numpy(), min=mn.numpy(), q_rowsum=q_rowsum, top2_gap=gap,
+        ref_quantize_seconds=t_ref, ref_threads=torch.get_num_threads(),
+    )
+    print(f"assign_{name}: B={B} M={M} reference quantize {t_ref:.1f} s on {torch.get_num_threads()} threads, "
+          f"min top2 gap {float(gap.astype(np.float32).min()):.3e} nn!=conc {np.mean(codes_nn != codes_conc):.3f}",
+          flush=True)
+
+
 def _dist_worker(rank, world, case, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", "29611"
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -147,6 +192,10 @@ def run_adc(name, case):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if "--big" in sys.argv:          # the two BASELINE-size cases only (minutes, tens of GB)
+        for name, case in GC.ASSIGN_BIG_CASES.items():
+            run_assign_big(name, case)
+        return
     for name, case in GC.ASSIGN_CASES.items():
         run_assign(name, case)
     for name, case in GC.DIST_CASES.items():
