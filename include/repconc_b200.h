@@ -230,6 +230,11 @@ void rc_adc_last_stats(int64_t out4[4]);
 void rc_adc_enable_timing(int enable);
 double rc_adc_last_scan_ms(void);
 int rc_adc_last_scan_launches(void);
+/* LSU (shared-memory data pipe) wavefronts the filtered-scan launches of the last search must issue, counted
+ * analytically from the kernel's instruction mix (the quantity ncu reports as
+ * l1tex__data_pipe_lsu_wavefronts), and the name of the scan kernel that ran */
+double rc_adc_last_scan_wavefronts(void);
+const char* rc_adc_last_scan_kernel(void);
 
 #ifdef __cplusplus
 }

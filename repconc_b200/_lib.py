@@ -60,6 +60,8 @@ SIGNATURES = {
     "rc_adc_enable_timing": (None, [c_int]),
     "rc_adc_last_scan_ms": (c_f64, []),
     "rc_adc_last_scan_launches": (c_int, []),
+    "rc_adc_last_scan_wavefronts": (c_f64, []),
+    "rc_adc_last_scan_kernel": (ctypes.c_char_p, []),
 }
 
 

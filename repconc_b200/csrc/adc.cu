@@ -42,6 +42,15 @@ constexpr int FB_ROWS = 4;            // exact-fallback queries per dense scan
 constexpr int64_t DENSE_N_MAX = 262144;  // corpora up to this size take the dense path
 constexpr int SAMPLE_BLK = 1024;      // sample = evenly spaced blocks of this many documents
 
+static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
+
+// optional CUDA-event timing of the filtered corpus scan (the dominant kernel) inside rc_adc_search
+static int g_timing = 0;
+static thread_local double g_scan_ms = 0.0;
+static thread_local int g_scan_launches = 0;
+static thread_local double g_scan_wavefronts = 0.0;     // analytic LSU wavefronts of the filtered-scan launches
+static thread_local const char* g_scan_kernel = "none";
+
 // ---------------------------------------------------------------------------------------------
 // LUT
 // ---------------------------------------------------------------------------------------------
@@ -582,6 +591,18 @@ static int launch_packed(PackScanArgs a, cudaStream_t st) {
     scan_splits(a.nq, qp, a.npos, a.M, &pps, &splits);
     a.pos_per_split = pps;
 #define RC_PSCAN(QP, MT) return launch_packed_inst<QP, MT>(a, (int)splits, st)
+    // LSU wavefronts of this launch (what ncu counts as l1tex__data_pipe_lsu_wavefronts): per warp and group of
+    // 4 documents x 8 queries the conflict-free kernel issues M/8 LDS.128 (4 wavefronts each), 4 exchange
+    // shuffles and 2 wavefronts of code bytes; the thread-per-document gather issues one 16 / 8 / 4-byte gather
+    // per (document, sub-vector) per tile at the measured 2.5 conflict wavefronts per ideal wavefront
+    const double tiles = (double)((a.nq + qp - 1) / qp);
+    if (qp == 8 && cf_capable(a.M) && !adc_force_gather()) {
+        g_scan_wavefronts += tiles * ((double)a.npos / 4.0) * (a.M / 2.0 + 6.0);
+        g_scan_kernel = "adc_scan_cf_kernel";
+    } else {
+        g_scan_wavefronts += tiles * ((double)a.npos / 32.0) * a.M * (qp * 2 / 4.0) * 2.5;
+        g_scan_kernel = "adc_scan_packed_kernel";
+    }
     if (qp == 8 && !adc_force_gather()) {
         switch (a.M) {   // conflict-free layout
             case 8: return launch_cf_inst<8>(a, (int)splits, st);
@@ -1073,12 +1094,6 @@ static int dense_topk(const AdcWs& w, int rows, int64_t N, int k, int k_eff, int
     return RC_OK;
 }
 
-static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
-
-// optional CUDA-event timing of the filtered corpus scan (the dominant kernel) inside rc_adc_search
-static int g_timing = 0;
-static thread_local double g_scan_ms = 0.0;
-static thread_local int g_scan_launches = 0;
 
 }  // namespace rc
 
@@ -1091,6 +1106,8 @@ RC_API void rc_adc_last_stats(int64_t out4[4]) {
 RC_API void rc_adc_enable_timing(int enable) { g_timing = enable ? 1 : 0; }
 RC_API double rc_adc_last_scan_ms(void) { return g_scan_ms; }
 RC_API int rc_adc_last_scan_launches(void) { return g_scan_launches; }
+RC_API double rc_adc_last_scan_wavefronts(void) { return g_scan_wavefronts; }
+RC_API const char* rc_adc_last_scan_kernel(void) { return g_scan_kernel; }
 
 RC_API int rc_adc_lut(const float* queries, int64_t ldq, const float* centroids, int64_t nq, int M, int K, int ds,
                       float* lut, void* stream) {
@@ -1158,6 +1175,8 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
     std::vector<unsigned int> cnt_h;
     g_scan_ms = 0.0;
     g_scan_launches = 0;
+    g_scan_wavefronts = 0.0;
+    g_scan_kernel = "none";
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (g_timing) {
         RC_CUDA(cudaEventCreate(&ev0));

@@ -56,17 +56,28 @@ def from_pq_to_ivfpq(indexpq):
 
 def load_index_to_gpu(index, single_gpu_id: Optional[int] = None):
     """evaluate_repconc.py:121-135: make the index device-resident (one H2D copy of N*M bytes).
-    One process drives one GPU here: without `single_gpu_id` the current CUDA device is used.
-    For the multi-GPU corpus-sharded search see `load_index_shard_to_gpu`."""
-    if isinstance(index, faiss.GpuIndexPQ):
+    `single_gpu_id` given: that device holds the whole index (reference :123-128).
+    `single_gpu_id` None: the reference clones the index onto ALL visible GPUs from this one process
+    (`index_cpu_to_all_gpus`, :130-134 -- replicas, queries split between them).  Here the corpus is SHARDED over
+    the visible devices instead (each device scans 1/n of the codes for every query, one host thread per device,
+    per-shard top-k merged on the first device): same results, n times the scan rate, and it is reached by the
+    unchanged evaluator, which searches from the main process only (run_repconc_eval.py:93-100,155).
+    RC_ADC_DEVICES=n limits the number of devices used."""
+    if isinstance(index, (faiss.GpuIndexPQ, faiss.MultiGpuIndexPQ)):
         return index
-    device = torch.device("cuda", torch.cuda.current_device() if single_gpu_id is None else single_gpu_id)
-    return faiss.GpuIndexPQ.from_host(index, device)
+    if single_gpu_id is None:
+        import os
+        n = torch.cuda.device_count()
+        n = min(n, int(os.environ.get("RC_ADC_DEVICES", n)))
+        if n > 1 and index.ntotal >= n:
+            return faiss.MultiGpuIndexPQ.from_host(index, list(range(n)))
+        return faiss.GpuIndexPQ.from_host(index, torch.device("cuda", torch.cuda.current_device()))
+    return faiss.GpuIndexPQ.from_host(index, torch.device("cuda", single_gpu_id))
 
 
 def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarray, index, topk: int):
     """evaluate_repconc.py:180-185."""
-    if (isinstance(index, faiss.GpuIndexPQ) and isinstance(query_embeds, np.ndarray)
+    if (isinstance(index, _DEVICE_INDEXES) and isinstance(query_embeds, np.ndarray)
             and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
         # position -> corpus id on the device, before the copy back (same values as :183)
         topk_scores, topk_ids = index.search(query_embeds, topk, corpus_ids=corpus_ids)
@@ -82,7 +93,7 @@ def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np
     """evaluate_repconc.py:188-206."""
     all_topk_scores, all_topk_ids = [], []
     iterations = math.ceil(len(query_ids) / batch_size)
-    if (iterations > 1 and isinstance(index, faiss.GpuIndexPQ) and isinstance(query_embeds, np.ndarray)
+    if (iterations > 1 and isinstance(index, _DEVICE_INDEXES) and isinstance(query_embeds, np.ndarray)
             and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
         # same batches (np.array_split, :193-197), searched back to back with the copy-back of one batch
         # overlapping the scan of the next
@@ -138,18 +149,68 @@ def merge_shard_results(all_scores: torch.Tensor, all_ids: torch.Tensor):
     return scores, ids
 
 
+class ShardedSearcher:
+    """Multi-PROCESS corpus-sharded search (one process per GPU, torch.distributed): wraps this rank's shard
+    (a GpuIndexPQ whose ids are global row positions) and runs the exchange after the local scan.
+
+    Every rank scans its shard for ALL queries (no collective touches the scan).  Then, instead of all-gathering
+    W full (nq, k) lists onto every rank and merging all of them everywhere, the queries are dealt out: rank r
+    OWNS the r-th block of ceil(nq / W) queries, one all_to_all brings it the W per-shard lists of its block
+    (12 B x nq x k x (W-1)/W sent and received per rank), it merges them (rc_topk_merge on nq / W queries), and
+    one all_gather of the merged blocks gives every rank the final (nq, k) result (12 B x nq x k received).
+    `search` takes and returns CUDA tensors; `search_batches` is the host-array pipeline behind batch_search
+    (only rank 0 maps ids and copies results back; the other ranks return empty arrays)."""
+
+    def __init__(self, shard_index, group=None):
+        self.shard = shard_index
+        self.group = group
+        self.device = shard_index.device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n = torch.tensor([shard_index.ntotal], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(n, group=group)
+        self.ntotal = int(n.item())
+        self.last_stats = None
+
+    def search(self, x, k, corpus_ids=None):
+        """CUDA tensor in -> CUDA tensors out on every rank; numpy in -> numpy out (rank 0; see search_batches)."""
+        k = int(k)
+        if not isinstance(x, torch.Tensor):
+            return self.search_batches([np.ascontiguousarray(x, dtype=np.float32)], k, corpus_ids=corpus_ids)
+        x = x.to(self.device)
+        s, i = self.shard.search_tensor(x, k)
+        self.last_stats = self.shard.last_stats
+        W = self.world
+        if W == 1:
+            return s, i
+        nq = s.shape[0]
+        nb = (nq + W - 1) // W                       # queries per owner
+        if nb * W != nq:                             # pad with empty lists
+            ps = torch.full((nb * W, k), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
+            pi = torch.full((nb * W, k), -1, dtype=i.dtype, device=i.device)
+            ps[:nq], pi[:nq] = s, i
+            s, i = ps, pi
+        rs, ri = torch.empty_like(s), torch.empty_like(i)
+        dist.all_to_all_single(rs, s, group=self.group)          # (W, nb, k): every shard's list of my block
+        dist.all_to_all_single(ri, i, group=self.group)
+        ms, mi = merge_shard_results(rs.view(W, nb, k), ri.view(W, nb, k))
+        fs, fi = torch.empty_like(s), torch.empty_like(i)
+        dist.all_gather_into_tensor(fs, ms, group=self.group)
+        dist.all_gather_into_tensor(fi, mi, group=self.group)
+        return fs[:nq], fi[:nq]
+
+    def search_tensor(self, x, k):
+        return self.search(x, k)
+
+    def search_batches(self, batches, k, corpus_ids=None):
+        return self.shard.search_batches(batches, k, corpus_ids=corpus_ids, search_fn=self.search,
+                                         copy_back=self.rank == 0)
+
+
+_DEVICE_INDEXES = (faiss.GpuIndexPQ, faiss.MultiGpuIndexPQ, ShardedSearcher)
+
+
 def sharded_search(shard_index, query_embeds, topk: int, group=None):
-    """Every rank scans its own shard for ALL queries, then one all_gather of the (nq, k) lists and a
-    k-way merge on every rank.  No collective touches the scan itself.  Returns CUDA tensors."""
-    if not isinstance(query_embeds, torch.Tensor):
-        query_embeds = torch.from_numpy(np.ascontiguousarray(query_embeds, dtype=np.float32))
-    q = query_embeds.to(shard_index.device)
-    s, i = shard_index.search_tensor(q, topk)
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        return s, i
-    gs = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
-    gi = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
-    dist.all_gather_into_tensor(gs, s, group=group)
-    dist.all_gather_into_tensor(gi, i, group=group)
-    return merge_shard_results(gs, gi)
+    """One corpus-sharded search over torch.distributed ranks (see ShardedSearcher).  Returns CUDA tensors."""
+    return ShardedSearcher(shard_index, group).search(query_embeds, topk)

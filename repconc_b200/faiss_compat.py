@@ -244,15 +244,15 @@ class GpuIndexPQ:
         return buf[:n].view(shape)
 
     def _resident_ids(self, corpus_ids):
-        """device copy of an external id table, cached per host array (pointer, length, dtype)"""
+        """device copy of an external id table.  The cache is validated against a PRIVATE host copy of the table
+        with a full comparison (one memcmp-speed pass, ~10 ms for 8.8 M ids, once per search / batch_search call):
+        any in-place edit of the caller's array, wherever it is, refreshes the device copy."""
         a = np.ascontiguousarray(corpus_ids)
         if a.dtype != np.int64:
             return None
-        # pointer + shape + a strided 1024-element fingerprint (catches in-place edits of the table)
-        key = (a.__array_interface__["data"][0], a.shape, hash(a[:: max(1, a.size // 1024)].tobytes()))
-        hit = self._ids_cache.get("key")
-        if hit != key:
-            self._ids_cache = {"key": key, "dev": torch.from_numpy(a).to(self.device), "ref": a}
+        hit = self._ids_cache
+        if not hit or hit["host"].shape != a.shape or not np.array_equal(hit["host"], a):
+            self._ids_cache = {"host": a.copy(), "dev": torch.from_numpy(a).to(self.device)}
         return self._ids_cache["dev"]
 
     def search(self, x, k, corpus_ids=None):
@@ -286,21 +286,25 @@ class GpuIndexPQ:
         return hs.numpy().copy(), hi.numpy().copy()
 
 
-    def search_batches(self, batches, k, corpus_ids=None):
+    def search_batches(self, batches, k, corpus_ids=None, search_fn=None, copy_back=True):
         """Pipelined `search` over a list of host query arrays (the loop of evaluate_repconc.batch_search,
         `:193-203`): while the GPU scans batch i+1, the results of batch i travel device -> pinned host on a copy
         stream and are written into their slice of the preallocated output.  Returns (scores (n,k) fp32,
-        ids (n,k) int64) for the concatenated batches -- value for value what per-batch `search` calls give."""
+        ids (n,k) int64) for the concatenated batches -- value for value what per-batch `search` calls give.
+        `search_fn(x_dev, k) -> (scores, ids)` replaces this index's own scan (multi-device / multi-process
+        searchers pass theirs); `copy_back=False` runs the searches but skips the id mapping and the copy-back
+        (ranks other than 0 of a sharded search) and returns empty arrays."""
         k = int(k)
+        search_fn = search_fn or self.search_tensor
         sizes = [int(len(b)) for b in batches]
         n = sum(sizes)
-        out_s = np.empty((n, k), np.float32)
-        out_i = np.empty((n, k), np.int64)
+        out_s = np.empty((n if copy_back else 0, k), np.float32)
+        out_i = np.empty((n if copy_back else 0, k), np.int64)
         if n == 0:
             return out_s, out_i
         with torch.cuda.device(self.device):
-            ids_dev = self._resident_ids(corpus_ids) if corpus_ids is not None else None
-            if corpus_ids is not None and ids_dev is None:
+            ids_dev = self._resident_ids(corpus_ids) if (corpus_ids is not None and copy_back) else None
+            if corpus_ids is not None and copy_back and ids_dev is None:
                 raise TypeError("search_batches: corpus_ids must be an int64 array")
             compute = torch.cuda.current_stream()
             if getattr(self, "_copy_stream", None) is None:
@@ -358,8 +362,11 @@ class GpuIndexPQ:
                 mark("staged")
                 xd = xd_group[lo - g_lo: lo - g_lo + nb]
                 mark("h2d")
-                s, i = self.search_tensor(xd, k)
+                s, i = search_fn(xd, k)
                 mark("search")
+                if not copy_back:
+                    lo += nb
+                    continue
                 if ids_dev is not None:
                     mapped = torch.empty_like(i)
                     _lib.check(_lib.load().rc_map_ids(i.data_ptr(), ids_dev.data_ptr(), ids_dev.numel(), i.numel(),
@@ -385,6 +392,81 @@ class GpuIndexPQ:
                     f.result()
             mark("drained")
         return out_s, out_i
+
+
+class MultiGpuIndexPQ:
+    """One process, several devices: the corpus is sharded contiguously over `shards` (GpuIndexPQ objects, one per
+    device, ids = global row positions).  A search sends the queries to every device (peer copies), one host
+    thread per device runs that shard's scan (ctypes releases the GIL, so the scans run concurrently), the
+    per-shard (nq, k) lists are copied to the first device and merged there by rc_topk_merge.
+    This is what `load_index_to_gpu(index)` returns when several GPUs are visible -- the counterpart of the
+    reference's `index_cpu_to_all_gpus` (evaluate_repconc.py:130-134), sharding instead of replicating."""
+
+    def __init__(self, shards):
+        assert len(shards) >= 1
+        self.shards = list(shards)
+        self.device = self.shards[0].device
+        self.M, self.dsub, self.d = self.shards[0].M, self.shards[0].dsub, self.shards[0].d
+        self.metric_type = METRIC_INNER_PRODUCT
+        self.is_trained = True
+        self.last_stats = None
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="repconc-shard")
+
+    @classmethod
+    def from_host(cls, index, devices):
+        n, W = index.ntotal, len(devices)
+        shards = []
+        for r, dev in enumerate(devices):
+            base, extra = divmod(n, W)
+            lo = r * base + min(r, extra)
+            hi = lo + base + (1 if r < extra else 0)
+            shards.append(GpuIndexPQ.from_host(index, torch.device("cuda", dev), lo, hi))
+        return cls(shards)
+
+    @property
+    def ntotal(self):
+        return sum(s.ntotal for s in self.shards)
+
+    def set_centroids(self, centroids):
+        for s in self.shards:
+            s.set_centroids(centroids.to(s.device))
+
+    def search_tensor(self, x, k):
+        k = int(k)
+        x = ops._rows_f32(x if x.is_cuda else x.to(self.device), "query_embeds")
+        torch.cuda.current_stream(x.device).synchronize()          # the queries are complete before other devices read them
+
+        def run(shard):
+            with torch.cuda.device(shard.device):
+                s, i = shard.search_tensor(x.to(shard.device), k)
+                if shard.device != self.device:
+                    s, i = s.to(self.device), i.to(self.device)
+                torch.cuda.current_stream(shard.device).synchronize()
+                return s, i, shard.last_stats
+        res = list(self._pool.map(run, self.shards))
+        self.last_stats = {key: sum(r[2][key] for r in res) if key in ("filtered", "dense") else
+                           max(r[2][key] for r in res) for key in res[0][2]}
+        if len(res) == 1:
+            return res[0][0], res[0][1]
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            ss = torch.stack([r[0] for r in res]).contiguous()
+            ii = torch.stack([r[1] for r in res]).contiguous()
+            nq = ss.shape[1]
+            scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            _lib.check(lib.rc_topk_merge(ss.data_ptr(), ii.data_ptr(), len(res), nq, k, scores.data_ptr(),
+                                         ids.data_ptr(), ops._stream()), "rc_topk_merge")
+        return scores, ids
+
+    def search(self, x, k, corpus_ids=None):
+        if isinstance(x, torch.Tensor):
+            return self.search_tensor(x, k)
+        return self.search_batches([np.ascontiguousarray(x, dtype=np.float32)], k, corpus_ids=corpus_ids)
+
+    def search_batches(self, batches, k, corpus_ids=None):
+        return self.shards[0].search_batches(batches, k, corpus_ids=corpus_ids, search_fn=self.search_tensor)
 
 
 # ----------------------------------------------------------------------------------------------
