@@ -118,15 +118,41 @@ int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int
 int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
                        int apply_rowsum, void* state, double* Q, int32_t* flags, void* stream);
 /* Single-rank solve = rc_sinkhorn_begin + (iters-1) x rc_sinkhorn_step + rc_sinkhorn_finish with
- * B_global == B, in one call and bit-identical to that sequence (the row-sum reduction and the row
- * normalisation fuse into one kernel per iteration because no all-reduce separates them).  This is
- * what RepCONC.quantize runs when torch.distributed is not initialised (modeling_repconc.py:61). */
+ * B_global == B, in one call and bit-identical to that sequence.  For the sparse passes (K == 256,
+ * dense == 0) the whole iteration loop is ONE persistent cooperative kernel: per sub-vector, the last
+ * CTA that finishes a pass reduces the row sums, updates the row scaling and releases the next pass --
+ * three launches per iteration become none.  This is what RepCONC.quantize runs when torch.distributed
+ * is not initialised (modeling_repconc.py:61). */
 int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
                       int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
                       void* stream);
+/* W-rank solve with the per-iteration exchange of the row sums FUSED into the persistent kernel: the
+ * `dist.all_reduce(sum_of_rows)` of modeling_repconc.py:156-157 (M x K fp64 every iteration) happens
+ * inside the pass that produces the sums -- the last CTA to finish sub-vector m publishes its 256 sums
+ * in a symmetric buffer, raises a flag on every peer (system-scope release store over NVLink), waits for
+ * the W flags, sums the W vectors in rank order straight from peer memory (bitwise identical on every
+ * rank) and updates the row scaling of m, while other sub-vectors are still being scanned.
+ *   peer_buffers_host  HOST array of W device pointers: rank p's symmetric buffer as mapped into THIS
+ *                      process, rc_sinkhorn_peer_buffer_bytes(M, K) bytes each, zero-initialised ONCE
+ *                      (e.g. torch.distributed._symmetric_memory); reused by later calls
+ *   seq_base           exchange sequence numbers consumed so far (0 for the first call, then the sum of
+ *                      max(iters, 1) over the previous calls on this buffer) -- the same on every rank
+ *   minmax             already all-reduced (MAX / MIN) by the caller, as for rc_sinkhorn_begin
+ * Sparse passes only (K == 256); a dense re-run goes through the step-wise entry points + the caller's
+ * all-reduce.  Waits are bounded (env RC_PEER_TIMEOUT_MS, default 30000): RC_FLAG_PEER_TIMEOUT. */
+size_t rc_sinkhorn_peer_buffer_bytes(int M, int K);
+int rc_sinkhorn_solve_peer(float* table, const float* minmax, int64_t B, int64_t B_global, int M, int K,
+                           double eps, int iters, void* state, const uint64_t* peer_buffers_host, int rank,
+                           int W, uint32_t seq_base, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
+                           void* stream);
 /* diagnostics of the survivor lists the sparse pass currently holds (K == 256 only): out[0] = entries,
- * out[1] = longest row, out[2] = rows, out[3 + i] = rows with i*8 <= count < i*8+8 (i < 33). `out` is a
- * DEVICE array of 36 int64. */
+ * out[1] = longest row, out[2] = rows, out[3 + i] = rows with i*8 <= count < i*8+8 (i < 33); counters of
+ * the last assignment on this state: out[36] = segments that ran the selection pass, out[37] = segments
+ * that ran the list pass, out[38] = centroids that failed the mass check, out[39] = rows that found the
+ * survivor pool full.  `out` is a DEVICE array of 40 int64. */
+/* diagnostics: per-CTA nanoseconds of the last persistent-kernel run (wait, selection, list, arrive+update);
+ * out_host is a HOST array of max_ctas x 4 int64; returns the number of CTAs written; synchronises the device */
+int rc_sinkhorn_debug_cta_times(void* state, int64_t B, int M, int K, int64_t* out_host, int max_ctas);
 int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream);
 /* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0
  * steps_done : number of rc_sinkhorn_step calls since rc_sinkhorn_begin (the last row sums get the sparse

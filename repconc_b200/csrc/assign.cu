@@ -300,24 +300,55 @@ __device__ __forceinline__ void bulk_load_row(float* dst_smem, const float* src,
 constexpr int SK_TILE = 2 * SK_WARPS;
 struct SkPart {
     int64_t tpm;    // row tiles per sub-vector = ceil(B / SK_TILE)
-    int64_t total;  // M * tpm
+    int64_t total;  // tiles of the range = (sub-vectors of the range) * tpm
     int G;          // CTAs
-    int S;          // max distinct sub-vectors one CTA can touch (partial slots)
+    int S;          // max distinct sub-vectors one CTA can touch inside the range (partial slots)
+    int m0;         // first sub-vector of the range (a tile index t of the range belongs to sub-vector m0 + t / tpm)
+    int slot0;      // partial rows of CTA g for this range: g * slots + slot0 + [0, S)
+    int slots;      // partial rows per CTA (all ranges)
 };
 
 __host__ __device__ inline int64_t sk_lo(const SkPart& p, int g) { return (p.total * g) / p.G; }
 
 constexpr int SK_MAX_CTAS_PER_SM = 4;  // partial buffer is sized for the largest grid any pass uses
 
+static int sk_part_slots(int64_t total, int64_t tpm, int G) {
+    const int64_t tpc = (total + G - 1) / G;
+    const int S = (int)((tpc + tpm - 2) / tpm) + 1;
+    return S < 2 ? 2 : S;
+}
+
 static SkPart sk_partition(int64_t B, int M, int ctas_per_sm = SK_CTAS_PER_SM) {
     SkPart p;
     p.tpm = (B + SK_TILE - 1) / SK_TILE;
     p.total = p.tpm * M;
     p.G = num_sms() * ctas_per_sm;
-    const int64_t tpc = (p.total + p.G - 1) / p.G;
-    p.S = (int)((tpc + p.tpm - 2) / p.tpm) + 1;
-    if (p.S < 2) p.S = 2;
+    p.S = sk_part_slots(p.total, p.tpm, p.G);
+    p.m0 = 0;
+    p.slot0 = 0;
+    p.slots = p.S;
     return p;
+}
+
+// Partition of the ITERATION passes (sparse path): the sub-vectors are cut into two halves and every CTA owns a
+// contiguous tile range in EACH half.  A CTA works through its range of half 0, then its range of half 1, pass
+// after pass; inside the persistent kernel the row-sum reduction / exchange / update of a half's sub-vectors
+// then runs while the CTAs are busy with the other half, instead of stalling them (a CTA's next pass over a
+// sub-vector needs that sub-vector's update, and with one contiguous range per CTA every CTA would wait for
+// the slowest CTA of its sub-vector plus the update latency in every pass).
+struct SkPart2 {
+    SkPart h[2];
+};
+
+static SkPart2 sk_partition2(int64_t B, int M, int ctas_per_sm) {
+    SkPart2 q;
+    const int64_t tpm = (B + SK_TILE - 1) / SK_TILE;
+    const int G = num_sms() * ctas_per_sm;
+    const int Ma = M / 2, Mb = M - Ma;
+    const int Sa = Ma > 0 ? sk_part_slots(tpm * Ma, tpm, G) : 0, Sb = sk_part_slots(tpm * Mb, tpm, G);
+    q.h[0] = SkPart{tpm, tpm * Ma, G, Sa, 0, 0, Sa + Sb};
+    q.h[1] = SkPart{tpm, tpm * Mb, G, Sb, Ma, Sa, Sa + Sb};
+    return q;
 }
 
 struct SkState {
@@ -327,13 +358,19 @@ struct SkState {
     double* partial;  // (G,S,K) per-CTA row-sum partials
     double* drift;    // (M,2)   {max_k, max_k - min_k} of lu - lu_build      (sparse pass)
     double* lu_build; // (M,K)   lu at the last survivor selection             (sparse pass)
-    unsigned long long* cursor;  // pool allocation cursor
+    unsigned long long* cursor;  // control block (see dec / arrive / abort_w)
+    unsigned int* dec;           // [0..1] done[h]: row-scaling updates completed in half h of the sub-vectors (all passes);
+                                 // [2 + 2h + (u & 1)] trig[h]: u + 1 if some sub-vector of half h asked, in update u, for
+                                 //     a new selection -> pass u re-selects the WHOLE half (everything else iterates on lists)
+    unsigned int* arrive;        // (M) CTAs that finished the current pass on m          (persistent kernel)
+    unsigned int* abort_w;       // (1) a bounded spin expired: every CTA leaves           (persistent kernel)
     uint2* csr;          // (M, tiles, SK_WARPS) row-pair directory: {pool record of the pair's first row in 16-byte
                          // units, sk_dir_word(survivors of row b, of row b + SK_WARPS)} (0: absent / did not fit);
                          // the second record follows the first one directly
     unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
-    uint64_t pool_cap;   // pool size in 16-byte units
+    unsigned long long* cta_ns;  // (G,4) diagnostics: ns per CTA in wait / selection / list / arrive+update
+    uint32_t row_cap;    // test hook: a row with more survivors than this raises RC_FLAG_SPARSE_UNSAFE (256 = never)
     double slack;        // selection depth beyond SK_MARGIN (log2 units)
 };
 
@@ -343,8 +380,10 @@ struct SkState {
 //   [64,..)   E = 2^(w - rowmax) of the survivors in (lane, j) order, padded to an even count
 // so a lane of the list pass finds its own survivors contiguous, with their columns implied by the mask:
 // no column index is stored, no per-column table is gathered and the row sums stay in registers.
-constexpr unsigned int SK_POOL_CHUNK = 1024;  // 16-byte units a warp grabs per atomic (16 KB; a full row is 132)
-constexpr int SK_POOL_PER_ROW = 160;  // survivor pool sized for this many entries per table row on average
+// Every row pair owns a FIXED slot of the pool, sized for two full records (2 x 2112 B): the address of a pair's
+// records follows from its index, nothing is allocated at run time, and the pool can never run out whatever the
+// data (only the bytes of the actual survivors are ever written or read).
+constexpr unsigned int SK_PAIR_BYTES = 2u * (64u + 8u * 256u);   // 4224
 __host__ __device__ constexpr uint32_t sk_record_units(uint32_t cnt) { return 4u + ((cnt + 1u) >> 1); }
 __device__ __forceinline__ int sp_col(int lane, int j) { return (j >> 2) * 128 + 4 * lane + (j & 3); }
 // Row-pair directory word: bytes of the first record (0 = absent) | bytes of both records << 12 | odd-count
@@ -375,8 +414,9 @@ static double sk_slack() {
     return v;
 }
 
-// test hook: usable survivor-pool capacity in entries per table row (0 = the allocation's SK_POOL_PER_ROW); lets a
-// test exhaust the pool on one rank only (rc_sinkhorn_debug_pool_entries)
+// test hook: pretend a row's record holds at most this many survivors (0 = no limit): a longer row raises
+// RC_FLAG_SPARSE_UNSAFE exactly as an exhausted pool would -- on one rank only, if only that rank sets it
+// (rc_sinkhorn_debug_pool_entries)
 static int64_t g_pool_entries_override = 0;
 
 static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, SkState* s) {
@@ -393,34 +433,34 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
     size_t pa = 0;
     for (int c = 1; c <= SK_MAX_CTAS_PER_SM; ++c) {
         const SkPart pc = sk_partition(B, M, c);
-        pa = std::max(pa, (size_t)pc.G * pc.S * K * 8);
+        const SkPart2 p2 = sk_partition2(B, M, c);
+        pa = std::max(pa, (size_t)pc.G * std::max(pc.slots, p2.h[0].slots) * K * 8);
     }
     (void)p;
     const size_t o_pa = take(pa);
-    const size_t o_drift = take((size_t)M * 16 + 16);   // + {int decision, int block counter}
+    const size_t o_drift = take((size_t)M * 16 + 16);
     const size_t o_lub = take((size_t)M * K * 8);
-    const size_t o_cur = take(256);
-    // every warp of the selection pass may strand up to one chunk
-    uint64_t pool = (uint64_t)M * (uint64_t)B * sk_record_units(SK_POOL_PER_ROW) +
-                    (uint64_t)num_sms() * SK_MAX_CTAS_PER_SM * SK_WARPS * SK_POOL_CHUNK;
-    if (pool > 0xFFFFFF00ull) pool = 0xFFFFFF00ull;      // record offsets are 32-bit
+    const size_t o_cur = take((size_t)M * 16 + 64 + 32);      // (M x u64, unused) | dec (M x u32) | arrive (M x u32) | abort,
+                                                         // diagnostics: selection / list segments, unsafe-mass, pool-full events
     const bool csr = (K == 256);
-    const size_t o_csr = take(csr ? (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS * 8 : 0);
+    const size_t pairs = (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS;
+    const size_t o_csr = take(csr ? pairs * 8 : 0);
     const size_t o_U = take((size_t)M * K * 8);
-    const size_t o_pool = take(csr ? (size_t)pool * 16 : 0);
+    const size_t o_dbg = take((size_t)num_sms() * SK_MAX_CTAS_PER_SM * 4 * 8);   // per-CTA phase times (diagnostics)
+    const size_t o_pool = take(csr ? pairs * SK_PAIR_BYTES : 0);
     if (s) {
         s->drift = (double*)(b + o_drift);
         s->lu_build = (double*)(b + o_lub);
         s->cursor = (unsigned long long*)(b + o_cur);
+        s->dec = (unsigned int*)(b + o_cur + (size_t)M * 8);      // 8 words: done[2], trig[2][2]
+        s->arrive = s->dec + 8;
+        s->abort_w = s->arrive + M;
         s->csr = (uint2*)(b + o_csr);
         s->U = (double*)(b + o_U);
+        s->cta_ns = (unsigned long long*)(b + o_dbg);
         s->pool = (unsigned char*)(b + o_pool);
         s->slack = sk_slack();
-        s->pool_cap = pool;
-        if (g_pool_entries_override > 0) {
-            const uint64_t cap = (uint64_t)M * (uint64_t)B * sk_record_units((uint32_t)g_pool_entries_override);
-            if (cap < s->pool_cap) s->pool_cap = cap;
-        }
+        s->row_cap = (g_pool_entries_override > 0 && g_pool_entries_override < 256) ? (uint32_t)g_pool_entries_override : 256u;
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
         s->lv = (double*)(b + o_lv);
@@ -655,258 +695,215 @@ sinkhorn_pass_kernel(float* __restrict__ table, const float* __restrict__ minmax
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sparse STEP pass (K == 256).  At the reference's eps (0.003) a column of Q spans hundreds of log2
+// Sparse passes (K == 256).  At the reference's eps (0.003) a column of Q spans hundreds of log2
 // units: only ~10 % of a table row lies within 2^-72 of the row's largest element (probed: 28 of 256
 // on synthetic data), and what lies below cannot change an fp64 column sum (dropped mass
 // <= 256 * 2^-72 = 2^-64 of the sum) nor -- as long as every centroid keeps a sane share of the mass,
-// which sinkhorn_update_kernel verifies (RC_FLAG_SPARSE_UNSAFE) -- an fp64 row sum.  Per row the warp
-//   1. evaluates log2 Q up to the column constant in fp32 for all 256 elements (2 x LDS.128 from the TMA
-//      ring, 8 FFMA) and takes the warp maximum,
-//   2. compacts the k of the elements within SK_MARGIN + 0.5 of that maximum (the 0.5 covers the fp32
-//      rounding, <= 2e-4) into a shared list by ballot / popc,
-//   3. evaluates those elements in fp64, one per lane: w = a + lu[k] - max, 2^w by Estrin's scheme,
-//   4. normalises by the column sum and adds Q / (B * sum) to the warp's private row-sum array.
+// which the row-scaling update verifies (RC_FLAG_SPARSE_UNSAFE) -- an fp64 row sum.
+//
+// SELECTION pass (sk_select_segment).  Lane l of the warp that owns a table row looks after the 8 columns
+// k(l,j) = (j>>2)*128 + 4*l + (j&3) it loaded (two float4 from the TMA ring).  Per row the warp
+//   1. evaluates log2 Q up to the column constant in fp32 for all 256 elements (8 FFMA per lane) and takes
+//      the warp maximum,
+//   2. keeps the elements within SK_MARGIN + slack + 0.5 of that maximum (the 0.5 covers the fp32 rounding,
+//      <= 2e-4): an 8-bit keep mask per lane, an exclusive scan of the per-lane counts,
+//   3. evaluates the kept elements in fp64 IN PLACE, lane by lane (w = a + lu[k] - max, 2^w by Estrin's scheme)
+//      -- no cross-lane compaction: the values land in the survivor record directly in (lane, j) order, the
+//      column sum is a butterfly over the per-lane sums and the row sums accumulate in REGISTERS (lane l owns
+//      columns k(l,j) for the whole segment),
+//   4. normalises by the column sum and adds Q / (B * sum) to its 8 row-sum accumulators.
 // The column scaling lv is not needed at all here: each column is normalised by its own sum, and the
 // row maximum keeps 2^w in range.  Accumulation order per (warp, k) is the row order -> deterministic.
+// (The previous version compacted the survivors across lanes by ballot, evaluated them 32 at a time and then
+//  re-ordered them into the lane-major record through shared memory: 560 instructions per row, a third of them
+//  the re-ordering; profiles/r01_sinkhorn_step_sparse_ncu.txt.)
 //
-// Survivor lists are REUSED across iterations.  The selection pass keeps everything within
-// SK_MARGIN + SK_SLACK of the row maximum and emits the (k, d~) pairs of each row into a pool (CSR: per-row
-// offset / count / fp32 maximum).  Between selections only lu changes: an element left out had
-// w - rowmax < -(MARGIN + SLACK) at selection time, and afterwards w - rowmax can grow by at most
-// spread = max_k(dlu) - min_k(dlu), dlu = lu - lu_build.  sinkhorn_update_kernel tracks that spread per
-// sub-vector; while max_m spread <= SK_SLACK the cheap pass (sinkhorn_step_list_kernel) iterates on the
-// lists alone -- no table read, no filter -- otherwise the selection pass runs again.  Both kernels are
-// launched every iteration and decide on the device (same inputs, same decision) which one works.
-// The dense kernel above remains the path for K != 256, for RC_SINKHORN_DENSE=1 and for the re-run
-// after RC_FLAG_SPARSE_UNSAFE.
+// Survivor lists are REUSED across iterations.  The selection keeps everything within SK_MARGIN + slack of the
+// row maximum and emits the E = 2^(w - rowmax) of each row as a record (layout above).  Between selections only
+// lu changes: an element left out had w - rowmax < -(MARGIN + slack) at selection time, and afterwards
+// w - rowmax can grow by at most spread = max_k(dlu) - min_k(dlu), dlu = lu - lu_build.  The row-scaling update
+// tracks that spread PER SUB-VECTOR; while spread_m <= slack the cheap LIST pass (sk_list_segment) iterates on
+// the lists of sub-vector m alone -- no table read, no filter -- otherwise m is selected again.  The decision
+// is one word per sub-vector (`dec[m]`), written by whoever updates the row scaling of m.
+// The dense kernel above remains the path for K != 256, for dense = 1 and for the re-run after
+// RC_FLAG_SPARSE_UNSAFE.
 // ---------------------------------------------------------------------------------------------
 constexpr double SK_MARGIN = 72.0;       // log2 units: dropped mass <= K * 2^-72 = 2^-64 of a column sum
-
-
-// true -> this iteration re-selects (and re-emits) the survivors; false -> it iterates on the lists
-// (the decision is made once per iteration by the last block of sinkhorn_update_kernel and published as
-//  one int behind the drift array: drift[2*M] reinterpreted)
-__device__ __forceinline__ bool csr_reselect(const double* __restrict__ drift, int M, int force) {
-    if (force) return true;
-    return reinterpret_cast<const int*>(drift + 2 * M)[0] != 0;
-}
-
 constexpr double SK_UNSAFE_LOG2 = -8.0;  // a row that keeps < 2^-8 / K of mass voids the row-sum bound
-constexpr int SP_CTAS_PER_SM = 3;
 constexpr int SP_K = 256;
-constexpr int SP_OFF_ACC = SK_WARPS * SK_DEPTH * SP_K * 4;          // ring: 32 KB
-constexpr int SP_OFF_Q = SP_OFF_ACC + SK_WARPS * SP_K * 8;          // acc : 16 KB
-constexpr int SP_OFF_LU = SP_OFF_Q + SK_WARPS * SP_K * 8;           // q   : 16 KB
-constexpr int SP_OFF_KL = SP_OFF_LU + SP_K * 8;                     // lu  :  2 KB
-constexpr int SP_OFF_BAR = SP_OFF_KL + SK_WARPS * SP_K;             // k   :  2 KB
-constexpr int SP_SMEM = SP_OFF_BAR + SK_WARPS * SK_DEPTH * 8;
+constexpr int LOOP_CTAS_PER_SM = 2;
 
-__global__ void __launch_bounds__(SK_THREADS, SP_CTAS_PER_SM)
-sinkhorn_step_sparse_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2,
-                            SkPart part, const double* __restrict__ lu_g, const double* __restrict__ drift,
-                            int force, SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
-    extern __shared__ __align__(128) unsigned char sp_smem[];
-    pdl_wait();
-    pdl_launch_dependents();
-    if (!csr_reselect(drift, M, force)) return;
+// shared memory of the iteration kernels: the list pass's ring of record slots and the selection pass's ring
+// of table rows share the same bytes (a CTA runs one pass at a time and every copy in flight is consumed before
+// the pass of a segment ends); the mbarriers are separate because the two rings have different depths
+constexpr int LP_DEPTH = 3;                                         // list pass: slots (row pairs) in flight per warp
+constexpr int LP_SLOT = 3072;                                       // bytes; a pair that does not fit is read from global
+constexpr int LOOP_RING_BYTES = SK_WARPS * LP_DEPTH * LP_SLOT;      // 72 KB  (selection needs SK_WARPS*SK_DEPTH*1 KB = 32 KB)
+static_assert(LOOP_RING_BYTES >= SK_WARPS * SK_DEPTH * SP_K * 4, "selection ring fits");
+constexpr int LOOP_OFF_RED = LOOP_RING_BYTES;                       // red : 16 KB, [warp][k] f64
+constexpr int LOOP_OFF_META = LOOP_OFF_RED + SK_WARPS * SP_K * 8;   // directory entry per list slot
+constexpr int LOOP_OFF_LBAR = LOOP_OFF_META + SK_WARPS * LP_DEPTH * 8;
+constexpr int LOOP_OFF_SBAR = LOOP_OFF_LBAR + SK_WARPS * LP_DEPTH * 8;
+constexpr int LOOP_OFF_MISC = LOOP_OFF_SBAR + SK_WARPS * SK_DEPTH * 8;   // update scratch: 16 doubles + 8 ints
+constexpr int LOOP_SMEM = LOOP_OFF_MISC + 16 * 8 + 8 * 8 + 32;
+
+struct SkRings {       // per-warp ring positions, live for the whole kernel
+    uint32_t sel_seq;                      // table rows consumed by the selection ring
+    uint32_t c_slot, c_phase, i_slot;      // list ring: next slot to consume (and its phase), next slot to fill
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const unsigned int* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Selection pass over one segment (rows of sub-vector m inside tiles [t, t_end)) -- see the comment above.
+// Writes the segment's row-sum partial (K doubles) to dst; ends with a block barrier.
+// (tile0, tile1) = the segment's tile range INSIDE sub-vector m.
+__device__ __forceinline__ void sk_select_segment(const float* __restrict__ table, int64_t B, double rBg, double scale2,
+                                                  int64_t tpm, const SkState& st, int m, int64_t tile0, int64_t tile1,
+                                                  unsigned char* smem, SkRings& rg, double* __restrict__ dst, int& bad) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* my_ring = reinterpret_cast<float*>(sp_smem) + warp * SK_DEPTH * SP_K;
-    double* acc_all = reinterpret_cast<double*>(sp_smem + SP_OFF_ACC);
-    double* my_acc = acc_all + warp * SP_K;
-    double* my_q = reinterpret_cast<double*>(sp_smem + SP_OFF_Q) + warp * SP_K;
-    double* lu_s = reinterpret_cast<double*>(sp_smem + SP_OFF_LU);
-    uint8_t* my_kl = sp_smem + SP_OFF_KL + warp * SP_K;
-    const uint32_t my_bars = smem_u32(sp_smem + SP_OFF_BAR) + warp * SK_DEPTH * 8;
-    const int g = blockIdx.x;
-    const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
-    if (t_lo >= t_hi) return;
-    const int m_first = (int)(t_lo / part.tpm);
-    int bad = 0;
-    uint32_t seq = 0;
-    if (lane == 0)
-        for (int d = 0; d < SK_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
-    fence_barrier_init();
-    __syncwarp();
+    float* my_ring = reinterpret_cast<float*>(smem) + warp * SK_DEPTH * SP_K;
+    const uint32_t my_bars = smem_u32(smem + LOOP_OFF_SBAR) + warp * SK_DEPTH * 8;
+    double* red_all = reinterpret_cast<double*>(smem + LOOP_OFF_RED);
+    const int64_t b_first = tile0 * SK_TILE + warp;
+    const int64_t b_stop = min(B, tile1 * SK_TILE);
+    const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
+    const float* tm = table + ((int64_t)m * B + b_first) * SP_K;   // this warp's first row
+    const int64_t pair0 = ((int64_t)m * tpm + tile0) * SK_WARPS + warp;   // index of this warp's first row pair
+    uint2* dir = st.csr + pair0;
     const float scale32 = (float)scale2;
-    const uint32_t row_bytes = SP_K * 4u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const float sel_margin = (float)(SK_MARGIN + st.slack) + 0.5f;
-    unsigned long long chunk_base = 0;   // this warp's current pool chunk
-    unsigned int chunk_left = 0;
+    const uint32_t row_bytes = SP_K * 4u;
+    uint32_t pair_cnt = 0u;
 
-    int64_t t = t_lo;
-    while (t < t_hi) {
-        const int m = (int)(t / part.tpm);
-        const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
-        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
-        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
-        const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
-        const float* tm = table + ((int64_t)m * B + b_first) * SP_K;   // this warp's first row
-        uint2* dir = st.csr + t * SK_WARPS + warp;                      // this warp's first row pair (tile t)
-        uint32_t pair_ptr = 0u, pair_cnt = 0u;
-
-        lu_s[threadIdx.x] = lu_g[(int64_t)m * SP_K + threadIdx.x];
+    double lu[8], A[8];
+    float lu32[8];
 #pragma unroll
-        for (int i = 0; i < SP_K / 32; ++i) my_acc[i * 32 + lane] = 0.0;
-        __syncthreads();
-        // this lane's 8 columns: k = 4*lane + j (j < 4) and 128 + 4*lane + (j - 4)
-        float lu32[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) lu32[j] = (float)lu_s[(j >> 2) * 128 + 4 * lane + (j & 3)];
-
-        if (lane == 0) {
-            const int pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
-            fence_proxy_async();
-            for (int d = 0; d < pre; ++d) {
-                const uint32_t slot = (seq + (uint32_t)d) % SK_DEPTH;
-                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)d * SK_WARPS * SP_K, row_bytes, my_bars + 8 * slot);
-            }
-        }
-        for (int r = 0; r < nrows; ++r) {
-            const uint32_t slot = seq % SK_DEPTH;
-            mbar_wait(my_bars + 8 * slot, (seq / SK_DEPTH) & 1u);
-            const float* src = my_ring + slot * SP_K;
-            // 1. fp32 log2 Q (up to the column constant) and its warp maximum
-            const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
-            const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
-            float wf[8];
-            wf[0] = fmaf(-d0.x, scale32, lu32[0]); wf[1] = fmaf(-d0.y, scale32, lu32[1]);
-            wf[2] = fmaf(-d0.z, scale32, lu32[2]); wf[3] = fmaf(-d0.w, scale32, lu32[3]);
-            wf[4] = fmaf(-d1.x, scale32, lu32[4]); wf[5] = fmaf(-d1.y, scale32, lu32[5]);
-            wf[6] = fmaf(-d1.z, scale32, lu32[6]); wf[7] = fmaf(-d1.w, scale32, lu32[7]);
-            float mx = fmaxf(fmaxf(fmaxf(wf[0], wf[1]), fmaxf(wf[2], wf[3])),
-                             fmaxf(fmaxf(wf[4], wf[5]), fmaxf(wf[6], wf[7])));
-            mx = warp_max(mx);
-            const float cutf = mx - sel_margin;
-            // 2. compaction by ballot
-            int base = 0;
-            uint32_t keep_mask = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool keep = wf[j] >= cutf;
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    my_kl[base + __popc(bal & lt_mask)] = (uint8_t)sp_col(lane, j);
-                    keep_mask |= 1u << j;
-                }
-                base += __popc(bal);
-            }
-            const int total = base;
-            // record header of this lane: survivors in the lanes below (exclusive scan) and the keep mask
-            uint32_t meta16;
-            {
-                const int c = __popc(keep_mask);
-                int incl = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                meta16 = ((uint32_t)(incl - c) << 8) | keep_mask;
-            }
-            __syncwarp();
-            // 3. fp64 evaluation of the survivors, shifted by the row maximum
-            const double shift = (double)mx;
-            double s = 0.0, q0 = 0.0;
-            int k0 = 0;
-            {
-                const bool valid = lane < total;
-                k0 = valid ? my_kl[lane] : 0;
-                const double w = fma(-(double)src[k0], scale2, lu_s[k0]) - shift;
-                q0 = valid ? exp2_fast_estrin(w) : 0.0;
-                s = q0;
-            }
-            for (int bs = 32; bs < total; bs += 32) {
-                const int idx = bs + lane;
-                const bool valid = idx < total;
-                const int k = valid ? my_kl[idx] : 0;
-                const double w = fma(-(double)src[k], scale2, lu_s[k]) - shift;
-                const double q = valid ? exp2_fast_estrin(w) : 0.0;
-                s += q;
-                my_q[idx] = q;
-            }
-            // 3b. emit the survivor list of this row: (k, 2^(w - rowmax)) pairs.  Pool space comes in per-warp
-            //     chunks (one atomic per ~50 rows); the order of rows in the pool is irrelevant, the order inside
-            //     a row is the ballot order -> deterministic sums
-            {
-                const unsigned int units = sk_record_units((uint32_t)total);
-                // the two records of a row pair (r even, r + 1) are contiguous in the pool: only the first row of
-                // a pair may open a new chunk, and it does so unless the largest possible second record fits too
-                const bool first = (r & 1) == 0;           // segments are tile-aligned: local parity = global parity
-                if (first && units + sk_record_units(SP_K) > chunk_left) {
-                    unsigned long long nb = 0;
-                    if (lane == 0) nb = atomicAdd(st.cursor, (unsigned long long)SK_POOL_CHUNK);
-                    chunk_base = __shfl_sync(0xffffffffu, nb, 0);
-                    chunk_left = SK_POOL_CHUNK;
-                }
-                const unsigned long long off = chunk_base;
-                const bool fits = off + (unsigned long long)units <= st.pool_cap;
-                unsigned char* rec = st.pool + (fits ? off : 0ull) * 16ull;
-                double* pe = reinterpret_cast<double*>(rec + 64);
-                if (fits) {
-                    reinterpret_cast<uint16_t*>(rec)[lane] = (uint16_t)meta16;
-                    if (lane == 0 && (total & 1)) pe[total] = 0.0;     // padding entry (copied, never used)
-                } else {
-                    bad |= RC_FLAG_SPARSE_UNSAFE;   // pool exhausted: the host re-runs densely
-                }
-                // survivor idx of the ballot order -> its place in (lane, j) order: the owner lane's header
-                // gives the lane's first entry, the mask bits below j the place inside the lane
-                for (int bs = 0; bs < total; bs += 32) {
-                    const int idx = bs + lane;
-                    const bool valid = idx < total;
-                    const int k = bs == 0 ? k0 : (valid ? (int)my_kl[idx] : 0);
-                    const double q = bs == 0 ? q0 : (valid ? my_q[idx] : 0.0);
-                    const int j = ((k >> 7) << 2) | (k & 3);
-                    const uint32_t hm = __shfl_sync(0xffffffffu, meta16, (k >> 2) & 31);
-                    if (valid && fits) pe[(hm >> 8) + __popc(hm & ((1u << j) - 1u))] = q;
-                }
-                // pair directory: written with the first row, completed with the second
-                const uint32_t cnt = fits ? (uint32_t)total : 0u;
-                uint32_t word;
-                if (first) {
-                    pair_ptr = (uint32_t)off;
-                    pair_cnt = cnt;
-                    word = sk_dir_word(cnt, 0u);
-                } else {
-                    if (pair_cnt == 0u) pair_ptr = (uint32_t)off;   // first record absent: the pair starts here
-                    word = sk_dir_word(pair_cnt, cnt);
-                }
-                if (lane == 0) dir[(int64_t)(r >> 1) * SK_WARPS] = make_uint2(pair_ptr, word);
-                chunk_base += (unsigned long long)units;
-                chunk_left -= units;
-            }
-            s = warp_sum(s);
-            if (!(s >= 0.5) || !isfinite(s)) bad |= RC_FLAG_NONFINITE;   // the maximum itself contributes ~1
-            // 4. Q / (B_global * column sum) into the row sums (:155, :162-163)
-            const double rz = __drcp_rn(s) * rBg;
-            if (lane < total) my_acc[k0] = fma(q0, rz, my_acc[k0]);
-            for (int bs = 32; bs < total; bs += 32) {
-                const int idx = bs + lane;
-                if (idx < total) {
-                    const int k = my_kl[idx];
-                    my_acc[k] = fma(my_q[idx], rz, my_acc[k]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && r + SK_DEPTH < nrows) {
-                fence_proxy_async();
-                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
-                              my_bars + 8 * slot);
-            }
-            ++seq;
-        }
-        __syncthreads();
-        {
-            double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * SP_K;
-            double sum = acc_all[threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < SK_WARPS; ++w) sum += acc_all[w * SP_K + threadIdx.x];
-            dst[threadIdx.x] = sum;
-        }
-        __syncthreads();
-        t = t_end;
+    for (int j = 0; j < 8; ++j) {
+        lu[j] = __ldcg(st.lu + (int64_t)m * SP_K + sp_col(lane, j));
+        lu32[j] = (float)lu[j];
+        A[j] = 0.0;
     }
-    if (bad) atomicOr(flags, bad);
+    if (lane == 0) {
+        const int pre = nrows < SK_DEPTH ? nrows : SK_DEPTH;
+        fence_proxy_async();
+        for (int d = 0; d < pre; ++d) {
+            const uint32_t slot = (rg.sel_seq + (uint32_t)d) % SK_DEPTH;
+            bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)d * SK_WARPS * SP_K, row_bytes, my_bars + 8 * slot);
+        }
+    }
+    for (int r = 0; r < nrows; ++r) {
+        const uint32_t slot = rg.sel_seq % SK_DEPTH;
+        mbar_wait(my_bars + 8 * slot, (rg.sel_seq / SK_DEPTH) & 1u);
+        const float* src = my_ring + slot * SP_K;
+        const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
+        const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        ++rg.sel_seq;
+        // 1. fp32 log2 Q (up to the column constant) and its warp maximum
+        float wf[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            wf[j] = fmaf(-dv[j], scale32, lu32[j]);
+            mx = fmaxf(mx, wf[j]);
+        }
+        mx = warp_max(mx);
+        const float cutf = mx - sel_margin;
+        // 2. keep mask, exclusive scan of the per-lane counts
+        uint32_t keep_mask = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) keep_mask |= (wf[j] >= cutf ? 1u : 0u) << j;
+        const int c = __popc(keep_mask);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - c;
+        // every lane's values of this row have gone through the shuffles above, i.e. its shared-memory loads have
+        // COMPLETED (issued is not enough: an asynchronous-proxy write must not overtake a generic read still queued
+        // in the load/store unit): the slot can be refilled
+        if (lane == 0 && r + SK_DEPTH < nrows)
+            bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
+                          my_bars + 8 * slot);
+        // the record: rows r (even) and r + 1 of this warp form a pair whose two records are contiguous in the
+        // pair's fixed slot of the pool (segments are tile-aligned: local parity = global parity)
+        const bool first = (r & 1) == 0;
+        const int64_t pair = pair0 + (int64_t)(r >> 1) * SK_WARPS;
+        unsigned char* rec = st.pool + (size_t)pair * SK_PAIR_BYTES + (first ? 0u : sk_record_bytes(pair_cnt));
+        double* pe_base = reinterpret_cast<double*>(rec + 64);
+        double* pe = pe_base + excl;
+        const bool fits = total > 0;
+        if (fits) {
+            reinterpret_cast<uint16_t*>(rec)[lane] = (uint16_t)(((uint32_t)excl << 8) | keep_mask);
+            if (lane == 0 && (total & 1)) pe_base[total] = 0.0;     // padding entry (copied, never used)
+        }
+        if ((uint32_t)total > st.row_cap) {                          // (test hook: simulated record capacity)
+            bad |= RC_FLAG_SPARSE_UNSAFE;
+            if (lane == 0) atomicAdd(st.abort_w + 4, 1u);
+        }
+        // 3. fp64 evaluation of this lane's survivors, shifted by the row maximum, straight into the record
+        const double shift = (double)mx;
+        double e[8];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            e[j] = 0.0;
+            if ((keep_mask >> j) & 1u) {
+                e[j] = exp2_fast_estrin(fma(-(double)dv[j], scale2, lu[j]) - shift);
+                s += e[j];
+                if (fits) *pe++ = e[j];
+            }
+        }
+        // pair directory: written with the first row, completed with the second
+        {
+            uint32_t word;
+            if (first) {
+                pair_cnt = (uint32_t)total;
+                word = sk_dir_word((uint32_t)total, 0u);
+            } else {
+                word = sk_dir_word(pair_cnt, (uint32_t)total);
+            }
+            if (lane == 0) dir[(int64_t)(r >> 1) * SK_WARPS] = make_uint2((uint32_t)pair, word);
+        }
+        s = warp_sum(s);
+        if (!(s >= 0.5) || !isfinite(s)) bad |= RC_FLAG_NONFINITE;   // the maximum itself contributes ~1
+        // 4. Q / (B_global * column sum) into the row sums (:155, :162-163)
+        const double rz = __drcp_rn(s) * rBg;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) A[j] = fma(e[j], rz, A[j]);
+    }
+    // the records are read back through the async proxy (cp.async.bulk) in later passes, possibly microseconds
+    // from now: the generic-proxy stores above must have been performed (fence) and ordered against that proxy
+    __threadfence();
+    fence_proxy_async_all();
+    // row sums of the segment: warp 0..7 in order (deterministic)
+    {
+        double* my_red = red_all + warp * SP_K;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) my_red[sp_col(lane, j)] = A[j];
+        __syncthreads();
+        double sum = red_all[threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < SK_WARPS; ++w) sum += red_all[w * SP_K + threadIdx.x];
+        __stcg(dst + threadIdx.x, sum);
+        __syncthreads();
+    }
 }
 
 // FINISH for K == 256: argmax_k (a + lu[k]) per table row with an fp32 pre-filter.  The warp evaluates the 256
@@ -969,10 +966,6 @@ sinkhorn_finish_sparse_kernel(const float* __restrict__ table, int64_t B, int M,
             const float4 d0 = reinterpret_cast<const float4*>(src)[lane];
             const float4 d1 = reinterpret_cast<const float4*>(src)[32 + lane];
             const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-            __syncwarp();                                    // the slot is in registers: refill it
-            if (lane == 0 && r + SK_DEPTH < nrows)
-                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
-                              my_bars + 8 * slot);
             ++seq;
             float wf[8];
             float mx = -INFINITY;
@@ -984,6 +977,11 @@ sinkhorn_finish_sparse_kernel(const float* __restrict__ table, int64_t B, int M,
                 mx = fmaxf(mx, wf[j]);
             }
             mx = warp_max(mx);
+            // every lane's values have gone through the reduction, i.e. the shared-memory loads have COMPLETED (an
+            // asynchronous-proxy write must not overtake a generic read still queued in the load/store unit): refill
+            if (lane == 0 && r + SK_DEPTH < nrows)
+                bulk_load_row(my_ring + slot * SP_K, tm + (int64_t)(r + SK_DEPTH) * SK_WARPS * SP_K, row_bytes,
+                              my_bars + 8 * slot);
             const bool slow = __any_sync(0xffffffffu, odd) || !(mx < 1000.0f) || !(mx > -3.0e38f);
             uint32_t cand = 0xffu;
             int code = -1;
@@ -1033,28 +1031,20 @@ sinkhorn_finish_sparse_kernel(const float* __restrict__ table, int64_t B, int M,
     if (bad) atomicOr(flags, bad);
 }
 
-// Iteration on the survivor lists alone (see the comment above sinkhorn_step_sparse_kernel).
+// Iteration on the survivor lists alone (see the comment above sk_select_segment).
 // A record carries E = 2^(w - rowmax) as evaluated (fp64) by the selection pass; since then only lu moved, so
 // the element's current value is E * 2^(lu[k] - lu_build[k]) -- up to a per-row constant that the column
-// normalisation removes.  U[k] = 2^(dlu[k] - max_k dlu) is evaluated once per iteration by
-// sinkhorn_update_kernel (256 values per sub-vector).
+// normalisation removes.  U[k] = 2^(dlu[k] - max_k dlu) is evaluated once per iteration by the row-scaling
+// update (256 values per sub-vector).
 // A warp owns a table row; lane l owns the 8 columns k(l,j) of the record layout, so its factors U[k(l,j)]
 // and its 8 row-sum accumulators live in REGISTERS for a whole sub-vector segment: per survivor the pass
 // issues one shared-memory load (the staged E) and two DFMAs -- no column gather, no read-modify-write of a
 // shared row-sum array (the kernel this replaces did three random 8-byte shared accesses per survivor and
 // sat at 78 % of the LSU wavefront limit, half of the wavefronts bank conflicts; profiles/r01_sinkhorn_list_*).
-// Records come in through a per-warp ring of cp.async.bulk copies (one per row, two rows per slot, LP_DEPTH
-// slots in flight, an mbarrier per slot).  Two rows are processed together so that the cross-lane reduction
-// (a transposing butterfly: 5 exchanges for both rows) and the reciprocal are shared.  The row sums are
-// accumulated as sum_b E * rz_b and multiplied by U[k] once per segment.  Every sum has a fixed order.
-constexpr int LP_CTAS_PER_SM = 2;
-constexpr int LP_DEPTH = 3;                                         // slots (row pairs) in flight per warp
-constexpr int LP_SLOT = 3072;                                       // bytes; a pair that does not fit is read from global
-constexpr int LP_OFF_RED = SK_WARPS * LP_DEPTH * LP_SLOT;           // ring: 64 KB
-constexpr int LP_OFF_META = LP_OFF_RED + SK_WARPS * SP_K * 8;       // red : 16 KB
-constexpr int LP_OFF_BAR = LP_OFF_META + SK_WARPS * LP_DEPTH * 8;   // directory entry per slot
-constexpr int LP_SMEM = LP_OFF_BAR + SK_WARPS * LP_DEPTH * 8;
-
+// Records come in through a per-warp ring of cp.async.bulk copies (one per row pair, LP_DEPTH slots in flight,
+// an mbarrier per slot).  Two rows are processed together so that the cross-lane reduction (a transposing
+// butterfly: 5 exchanges for both rows) and the reciprocal are shared.  The row sums are accumulated as
+// sum_b E * rz_b and multiplied by U[k] once per segment.  Every sum has a fixed order.
 
 // this lane's survivors of one row: e[j] = E of column k(lane,j) or 0; returns sum_j e[j] * U[j]
 __device__ __forceinline__ double lp_gather_row(const unsigned char* rec, uint32_t hm, const double (&U)[8],
@@ -1074,159 +1064,129 @@ __device__ __forceinline__ double lp_gather_row(const unsigned char* rec, uint32
     return sa + sb;
 }
 
-__global__ void __launch_bounds__(SK_THREADS, LP_CTAS_PER_SM)
-sinkhorn_step_list_kernel(int64_t B, double rBg, int M, SkPart part, const double* __restrict__ drift, int force,
-                          SkState st, double* __restrict__ partial, int32_t* __restrict__ flags) {
-    extern __shared__ __align__(128) unsigned char lp_smem[];
-    pdl_wait();
-    pdl_launch_dependents();
-    if (csr_reselect(drift, M, force)) return;
+__device__ __forceinline__ void sk_list_segment(int64_t B, double rBg, int64_t tpm, const SkState& st, int m,
+                                                int64_t tile0, int64_t tile1, unsigned char* smem, SkRings& rg,
+                                                double* __restrict__ dst, int& bad) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* my_ring = lp_smem + warp * LP_DEPTH * LP_SLOT;
-    double* red_all = reinterpret_cast<double*>(lp_smem + LP_OFF_RED);
-    uint2* my_meta = reinterpret_cast<uint2*>(lp_smem + LP_OFF_META) + warp * LP_DEPTH;
-    const uint32_t my_bars = smem_u32(lp_smem + LP_OFF_BAR) + warp * LP_DEPTH * 8;
-    const int g = blockIdx.x;
-    const int64_t t_lo = sk_lo(part, g), t_hi = sk_lo(part, g + 1);
-    if (t_lo >= t_hi) return;
-    const int m_first = (int)(t_lo / part.tpm);
-    int bad = 0;
-    // ring positions of this warp: next slot to consume (and its mbarrier phase), next slot to fill
-    uint32_t c_slot = 0, c_phase = 0, i_slot = 0;
-    if (lane == 0)
-        for (int d = 0; d < LP_DEPTH; ++d) mbar_init(my_bars + 8 * d, 1);
-    fence_barrier_init();
+    unsigned char* my_ring = smem + warp * LP_DEPTH * LP_SLOT;
+    double* red_all = reinterpret_cast<double*>(smem + LOOP_OFF_RED);
+    uint2* my_meta = reinterpret_cast<uint2*>(smem + LOOP_OFF_META) + warp * LP_DEPTH;
+    const uint32_t my_bars = smem_u32(smem + LOOP_OFF_LBAR) + warp * LP_DEPTH * 8;
+    // rows of this warp inside the segment: b = b_first + SK_WARPS * i, i < nrows (the rows this same warp wrote
+    // back to back into its pool chunks when it selected the segment)
+    const int64_t b_first = tile0 * SK_TILE + warp;
+    const int64_t b_stop = min(B, tile1 * SK_TILE);
+    const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
+    const int npairs = (nrows + 1) >> 1;
+    const int64_t pair0 = ((int64_t)m * tpm + tile0) * SK_WARPS + warp;   // this warp's first row pair
+    const uint2* dir = st.csr + pair0;
+    double U[8], A[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        U[j] = __ldcg(st.U + (int64_t)m * SP_K + sp_col(lane, j));
+        A[j] = 0.0;
+    }
+    // lane 0 holds the directory entry of the next pair to issue, fetched one pair ahead
+    // (no proxy fence before a refill: the slot was only READ through the generic proxy, and those loads have
+    //  delivered their values to the arithmetic before the __syncwarp that precedes the refill)
+    uint2 dn = make_uint2(0u, 0u);
+    auto fetch_meta = [&](int pair) {
+        if (lane == 0) dn = pair < npairs ? dir[(int64_t)pair * SK_WARPS] : make_uint2(0u, 0u);
+    };
+    auto issue = [&](int pair) {
+        const uint32_t slot = rg.i_slot;
+        if (lane == 0) {
+            const uint32_t tot = sk_dir_total(dn.y);
+            const uint32_t bar = my_bars + 8 * slot;
+            my_meta[slot] = make_uint2((uint32_t)pair, dn.y);
+            const bool staged = tot <= (uint32_t)LP_SLOT;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(staged ? tot : 0u)
+                         : "memory");
+            if (staged && tot)
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(my_ring + slot * LP_SLOT)),
+                    "l"(st.pool + (size_t)(pair0 + (int64_t)pair * SK_WARPS) * SK_PAIR_BYTES), "r"(tot), "r"(bar)
+                    : "memory");
+        }
+        fetch_meta(pair + 1);
+        rg.i_slot = rg.i_slot + 1 == LP_DEPTH ? 0u : rg.i_slot + 1;
+    };
+    if (lane == 0) fence_proxy_async();          // the ring bytes may last have been touched by generic accesses
+    fetch_meta(0);
+    for (int q = 0; q < npairs && q < LP_DEPTH; ++q) issue(q);
     __syncwarp();
 
-    int64_t t = t_lo;
-    while (t < t_hi) {
-        const int m = (int)(t / part.tpm);
-        const int64_t t_end = min(t_hi, (int64_t)(m + 1) * part.tpm);
-        // rows of this warp inside the segment: b = b_first + SK_WARPS * i, i < nrows (the rows warp `warp` of
-        // some selection CTA wrote back to back into its pool chunk)
-        const int64_t b_first = (t - (int64_t)m * part.tpm) * SK_TILE + warp;
-        const int64_t b_stop = min(B, (t_end - (int64_t)m * part.tpm) * SK_TILE);
-        const int nrows = b_first < b_stop ? (int)((b_stop - b_first + SK_WARPS - 1) / SK_WARPS) : 0;
-        const int npairs = (nrows + 1) >> 1;
-        const uint2* dir = st.csr + t * SK_WARPS + warp;                 // this warp's first row pair (tile t)
-        double U[8], A[8];
+    for (int q = 0; q < npairs; ++q) {
+        const uint32_t slot = rg.c_slot;
+        mbar_wait(my_bars + 8 * slot, rg.c_phase);
+        const uint2 mt = my_meta[slot];                     // {record of the pair, sk_dir_word}
+        const uint32_t len0 = sk_dir_len0(mt.y), tot = sk_dir_total(mt.y);
+        const uint32_t cnt0 = len0, cnt1 = tot - len0;      // (only their being zero / non-zero is used below)
+        uint32_t hm0 = 0u, hm1 = 0u;
+        double e0[8], e1[8], s0, s1;
+        if (tot <= (uint32_t)LP_SLOT) {                     // (two code paths: shared / global address space)
+            const unsigned char* rec0 = my_ring + slot * LP_SLOT;
+            const unsigned char* rec1 = rec0 + len0;
+            if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+            if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+            s0 = lp_gather_row(rec0, hm0, U, e0);
+            s1 = lp_gather_row(rec1, hm1, U, e1);
+        } else {                                            // oversized pair (rare): straight from the pool
+            const unsigned char* rec0 = st.pool + (size_t)(pair0 + (int64_t)mt.x * SK_WARPS) * SK_PAIR_BYTES;
+            const unsigned char* rec1 = rec0 + len0;
+            if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
+            if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
+            s0 = lp_gather_row(rec0, hm0, U, e0);
+            s1 = lp_gather_row(rec1, hm1, U, e1);
+        }
+        // column sums of both rows: lanes 0-15 end up with row 0's, lanes 16-31 with row 1's
+        const bool hi = lane & 16;
+        double a = hi ? s1 : s0;
+        a += __shfl_xor_sync(0xffffffffu, hi ? s0 : s1, 16);
+        // every lane's partial sums -- hence every value it loaded from the slot -- went through the exchange above:
+        // the shared-memory loads have COMPLETED (issued is not enough: an asynchronous-proxy write must not overtake
+        // a generic read still queued in the load/store unit), so the slot can be refilled LP_DEPTH pairs ahead
+        if (q + LP_DEPTH < npairs) issue(q + LP_DEPTH);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        const bool live = (hi ? cnt1 : cnt0) != 0u;
+        if (live && (!(a > 0.0) || !isfinite(a))) bad |= RC_FLAG_NONFINITE;
+        const double rz = live ? __drcp_rn(a) * rBg : 0.0;      // Q / (B_global * column sum)  (:162-163)
+        const double rz0 = __shfl_sync(0xffffffffu, rz, 0), rz1 = __shfl_sync(0xffffffffu, rz, 16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            U[j] = st.U[(int64_t)m * SP_K + sp_col(lane, j)];
-            A[j] = 0.0;
+            A[j] = fma(e0[j], rz0, A[j]);
+            A[j] = fma(e1[j], rz1, A[j]);
         }
-        // lane 0 holds the directory entry of the next pair to issue, fetched one pair ahead
-        // (no proxy fence before a refill: the slot was only READ through the generic proxy, and those loads have
-        //  delivered their values to the arithmetic before the __syncwarp that precedes the refill)
-        uint2 dn = make_uint2(0u, 0u);
-        auto fetch_meta = [&](int pair) {
-            if (lane == 0) dn = pair < npairs ? dir[(int64_t)pair * SK_WARPS] : make_uint2(0u, 0u);
-        };
-        auto issue = [&](int pair) {
-            const uint32_t slot = i_slot;
-            if (lane == 0) {
-                const uint32_t tot = sk_dir_total(dn.y);
-                const uint32_t bar = my_bars + 8 * slot;
-                my_meta[slot] = dn;
-                const bool staged = tot <= (uint32_t)LP_SLOT;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(staged ? tot : 0u)
-                             : "memory");
-                if (staged && tot)
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                            smem_u32(my_ring + slot * LP_SLOT)),
-                        "l"(st.pool + (size_t)dn.x * 16), "r"(tot), "r"(bar)
-                        : "memory");
-            }
-            fetch_meta(pair + 1);
-            i_slot = i_slot + 1 == LP_DEPTH ? 0u : i_slot + 1;
-        };
-        fetch_meta(0);
-        for (int q = 0; q < npairs && q < LP_DEPTH; ++q) issue(q);
-        __syncwarp();
-
-        for (int q = 0; q < npairs; ++q) {
-            const uint32_t slot = c_slot;
-            mbar_wait(my_bars + 8 * slot, c_phase);
-            const uint2 mt = my_meta[slot];                     // {record of the pair, sk_dir_word}
-            const uint32_t len0 = sk_dir_len0(mt.y), tot = sk_dir_total(mt.y);
-            const uint32_t cnt0 = len0, cnt1 = tot - len0;      // (only their being zero / non-zero is used below)
-            uint32_t hm0 = 0u, hm1 = 0u;
-            double e0[8], e1[8], s0, s1;
-            if (tot <= (uint32_t)LP_SLOT) {                     // (two code paths: shared / global address space)
-                const unsigned char* rec0 = my_ring + slot * LP_SLOT;
-                const unsigned char* rec1 = rec0 + len0;
-                if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
-                if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
-                s0 = lp_gather_row(rec0, hm0, U, e0);
-                s1 = lp_gather_row(rec1, hm1, U, e1);
-            } else {                                            // oversized pair (rare): straight from the pool
-                const unsigned char* rec0 = st.pool + (size_t)mt.x * 16;
-                const unsigned char* rec1 = rec0 + len0;
-                if (cnt0) hm0 = reinterpret_cast<const uint16_t*>(rec0)[lane];
-                if (cnt1) hm1 = reinterpret_cast<const uint16_t*>(rec1)[lane];
-                s0 = lp_gather_row(rec0, hm0, U, e0);
-                s1 = lp_gather_row(rec1, hm1, U, e1);
-            }
-            // both records are in registers: refill the slot LP_DEPTH pairs ahead before the reduction
-            __syncwarp();
-            if (q + LP_DEPTH < npairs) issue(q + LP_DEPTH);
-            // column sums of both rows: lanes 0-15 end up with row 0's, lanes 16-31 with row 1's
-            const bool hi = lane & 16;
-            double a = hi ? s1 : s0;
-            a += __shfl_xor_sync(0xffffffffu, hi ? s0 : s1, 16);
-            a += __shfl_xor_sync(0xffffffffu, a, 8);
-            a += __shfl_xor_sync(0xffffffffu, a, 4);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            const bool live = (hi ? cnt1 : cnt0) != 0u;
-            if (live && (!(a > 0.0) || !isfinite(a))) bad |= RC_FLAG_NONFINITE;
-            const double rz = live ? __drcp_rn(a) * rBg : 0.0;      // Q / (B_global * column sum)  (:162-163)
-            const double rz0 = __shfl_sync(0xffffffffu, rz, 0), rz1 = __shfl_sync(0xffffffffu, rz, 16);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                A[j] = fma(e0[j], rz0, A[j]);
-                A[j] = fma(e1[j], rz1, A[j]);
-            }
-            c_slot = c_slot + 1 == LP_DEPTH ? 0u : c_slot + 1;
-            c_phase ^= c_slot == 0 ? 1u : 0u;
-        }
-        // row sums of the segment: warp 0..7 in order (deterministic)
-        {
-            double* my_red = red_all + warp * SP_K;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) my_red[sp_col(lane, j)] = U[j] * A[j];
-            __syncthreads();
-            double* dst = partial + ((int64_t)g * part.S + (m - m_first)) * SP_K;
-            double sum = red_all[threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < SK_WARPS; ++w) sum += red_all[w * SP_K + threadIdx.x];
-            dst[threadIdx.x] = sum;
-            __syncthreads();
-        }
-        t = t_end;
+        rg.c_slot = rg.c_slot + 1 == LP_DEPTH ? 0u : rg.c_slot + 1;
+        rg.c_phase ^= rg.c_slot == 0 ? 1u : 0u;
     }
-    if (bad) atomicOr(flags, bad);
+    // row sums of the segment: warp 0..7 in order (deterministic)
+    {
+        double* my_red = red_all + warp * SP_K;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) my_red[sp_col(lane, j)] = U[j] * A[j];
+        __syncthreads();
+        double sum = red_all[threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < SK_WARPS; ++w) sum += red_all[w * SP_K + threadIdx.x];
+        __stcg(dst + threadIdx.x, sum);
+        __syncthreads();
+    }
 }
 
-// P[m,k] = sum over the CTAs that touched sub-vector m, in CTA order (deterministic).  One block per m.
-// The rows of `partial` that hold sub-vector m are located once per block (they belong to a contiguous range of
-// CTAs), then every thread sums its columns over that list with independent loads.
+// P[m,k] = sum over the CTAs that touched sub-vector m, in CTA order (deterministic); executed by one block.
+// The rows of `partial` that hold sub-vector m are located once (they belong to a contiguous range of CTAs),
+// then every thread sums its columns over that list with independent loads (L2: the partials come from other
+// SMs, possibly within the same kernel).
 constexpr int SK_RED_LIST = 256;
-__device__ __forceinline__ void sk_reduce_block(const double* __restrict__ partial, const SkPart& part_in,
-                                                const SkPart& part_list, int K, double* __restrict__ P, int csr_mode,
-                                                int M, int force, const SkState& st, int* s_off) {
-    const int m = blockIdx.x;
-    // the partials were written by the pass that did the work: the list pass has its own grid
-    const bool resel = csr_mode && csr_reselect(st.drift, M, force);
-    const SkPart part = (csr_mode && !resel) ? part_list : part_in;
-    if (csr_mode) {
-        // the pass that just ran re-selected the survivors iff csr_reselect() says so: remember its lu
-        if (resel)
-            for (int k = threadIdx.x; k < K; k += blockDim.x) st.lu_build[(int64_t)m * K + k] = st.lu[(int64_t)m * K + k];
-        if (m == 0 && threadIdx.x == 0) *st.cursor = 0ull;   // only live during a selection pass
-    }
-    const int64_t m_lo = (int64_t)m * part.tpm, m_hi = m_lo + part.tpm;
+__device__ __forceinline__ void sk_reduce_m(int m, const double* __restrict__ partial, const SkPart& part, int K,
+                                            double* __restrict__ P, int* s_off) {
+    const int ml = m - part.m0;                              // sub-vector index inside the range
+    const int64_t m_lo = (int64_t)ml * part.tpm, m_hi = m_lo + part.tpm;
     // only CTAs whose tile range [total*g/G, total*(g+1)/G) can touch [m_lo, m_hi)
     int g_first = (int)((m_lo * part.G) / part.total) - 1;
     int g_last = (int)((m_hi * part.G) / part.total) + 1;
@@ -1240,7 +1200,7 @@ __device__ __forceinline__ void sk_reduce_block(const double* __restrict__ parti
             const int g = g0 + i;
             const int64_t lo = sk_lo(part, g), hi = sk_lo(part, g + 1);
             const bool hit = lo < hi && hi > m_lo && lo < m_hi;
-            s_off[i] = hit ? g * part.S + (m - (int)(lo / part.tpm)) : -1;
+            s_off[i] = hit ? g * part.slots + part.slot0 + (ml - (int)(lo / part.tpm)) : -1;
         }
         __syncthreads();
 #pragma unroll
@@ -1250,7 +1210,7 @@ __device__ __forceinline__ void sk_reduce_block(const double* __restrict__ parti
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
                     const int o = s_off[i];
-                    if (o >= 0) sum[c] += partial[(int64_t)o * K + k];
+                    if (o >= 0) sum[c] += __ldcg(partial + (int64_t)o * K + k);
                 }
             }
         }
@@ -1258,109 +1218,372 @@ __device__ __forceinline__ void sk_reduce_block(const double* __restrict__ parti
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const int k = threadIdx.x + c * 256;
-        if (k < K) P[(int64_t)m * K + k] = sum[c];
+        if (k < K) __stcg(P + (int64_t)m * K + k, sum[c]);
     }
 }
 
-__global__ void __launch_bounds__(256)
-sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart part_in, SkPart part_list, int K,
-                       double* __restrict__ P, int csr_mode, int M, int force, SkState st) {
-    __shared__ int s_off[SK_RED_LIST];
-    pdl_wait();
-    pdl_launch_dependents();
-    sk_reduce_block(partial, part_in, part_list, K, P, csr_mode, M, force, st, s_off);
+// number of CTAs of the partition whose tile range touches sub-vector m (the arrivals its reduction waits for)
+__device__ __forceinline__ int sk_ctas_of_m(const SkPart& part, int m) {
+    const int64_t m_lo = (int64_t)(m - part.m0) * part.tpm, m_hi = m_lo + part.tpm;
+    int g_first = (int)((m_lo * part.G) / part.total) - 1;
+    int g_last = (int)((m_hi * part.G) / part.total) + 1;
+    if (g_first < 0) g_first = 0;
+    if (g_last > part.G - 1) g_last = part.G - 1;
+    int n = 0;
+    for (int g = g_first; g <= g_last; ++g) {
+        const int64_t lo = sk_lo(part, g), hi = sk_lo(part, g + 1);
+        n += (lo < hi && hi > m_lo && lo < m_hi) ? 1 : 0;
+    }
+    return n;
 }
 
-// row normalisation in log2 form: lu[m,k] -= log2(K * P[m,k])     (Q /= sum_of_rows; Q /= K, :158-159)
-// Also tracks, per sub-vector, how far lu has moved since the last survivor selection
-// (drift[m] = {max_k, max_k - min_k} of lu - lu_build), which is what decides between the list pass and a
-// new selection, and checks that every centroid kept a sane share of the mass through the last column
-// normalisation (the premise of the sparse pass's row-sum bound).  One block per m.
-__device__ __forceinline__ void sk_update_block(double* __restrict__ lu, const double* __restrict__ P,
-                                                const double* __restrict__ lu_build, int K, double Kd,
-                                                int check_mass, double slack, double* __restrict__ drift,
-                                                double* __restrict__ U, int32_t* __restrict__ flags, double* red_mx,
-                                                double* red_mn, double* s_dmax) {
-    const int m = blockIdx.x;
+// pass `it` on half h selects (true) or iterates on the lists (false); valid once every update `it` of the half is done
+__device__ __forceinline__ bool sk_pass_selects(const SkState& st, int h, unsigned int it) {
+    return it == 0u || __ldcg(st.dec + 2 + 2 * h + (it & 1u)) == it + 1u;
+}
+
+// Row normalisation of sub-vector m in log2 form: lu[m,k] -= log2(K * P[m,k])   (Q /= sum_of_rows; Q /= K, :158-159),
+// executed by one block; u = index of the update (0 follows BEGIN, u follows pass u - 1).  For the sparse passes it
+// also
+//   * remembers lu as lu_build when the pass that just ran on m was a selection,
+//   * measures how far lu has moved since the survivors of m were selected (spread = max_k - min_k of lu - lu_build)
+//     and, if that exceeds the selection slack, asks for a new selection: the request goes to the sub-vector's HALF
+//     (trig[h], see SkPart2) -- all sub-vectors of a half re-select in the same pass, so that the (4x longer)
+//     selection passes run side by side instead of each stalling everybody who waits for its sub-vector,
+//   * evaluates the per-column factors U = 2^(dlu - max dlu) the list pass needs,
+//   * checks that every centroid kept a sane share of the mass through the last column normalisation (the premise
+//     of the sparse pass's row-sum bound),
+//   * and counts itself done (release): pass u on the half may start once all its sub-vectors are.
+__device__ __forceinline__ void sk_update_m(int m, const SkState& st, int K, int check_mass, int sparse, int h,
+                                            unsigned int u, int32_t* __restrict__ flags, double* s_red /* >= 18 */) {
+    const bool was_sel = sparse && u >= 1u && sk_pass_selects(st, h, u - 1u);
     double dmax = -INFINITY, dmin = INFINITY;
     int bad = 0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const int64_t i = (int64_t)m * K + k;
-        const double z = Kd * P[i];
+        const double z = (double)K * __ldcg(st.P + i);
         if (!(z > 0.0) || !isfinite(z)) bad |= RC_FLAG_NONFINITE;
         const double dl = -log2(z);
-        if (check_mass && dl > -SK_UNSAFE_LOG2) bad |= RC_FLAG_SPARSE_UNSAFE;   // K*P[k] < 2^-8
-        const double nl = lu[i] + dl;
-        lu[i] = nl;
-        const double dv = nl - lu_build[i];
-        dmax = fmax(dmax, dv);
-        dmin = fmin(dmin, dv);
+        if (check_mass && dl > -SK_UNSAFE_LOG2) {                               // K*P[k] < 2^-8
+            bad |= RC_FLAG_SPARSE_UNSAFE;
+            atomicAdd(st.abort_w + 3, 1u);
+        }
+        const double lo = __ldcg(st.lu + i);
+        const double nl = lo + dl;
+        __stcg(st.lu + i, nl);
+        if (sparse) {
+            double lb;
+            if (was_sel) {
+                lb = lo;                                  // the selection that just ran used this lu
+                __stcg(st.lu_build + i, lb);
+            } else {
+                lb = __ldcg(st.lu_build + i);
+            }
+            const double dv = nl - lb;
+            dmax = fmax(dmax, dv);
+            dmin = fmin(dmin, dv);
+        }
     }
+    if (bad) atomicOr(flags, bad);
+    if (!sparse) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
         dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
     }
-    if ((threadIdx.x & 31) == 0) { red_mx[threadIdx.x >> 5] = dmax; red_mn[threadIdx.x >> 5] = dmin; }
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = dmax; s_red[8 + (threadIdx.x >> 5)] = dmin; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            dmax = fmax(dmax, red_mx[w]);
-            dmin = fmin(dmin, red_mn[w]);
+            dmax = fmax(dmax, s_red[w]);
+            dmin = fmin(dmin, s_red[8 + w]);
         }
-        drift[2 * m] = dmax;
-        drift[2 * m + 1] = dmax - dmin;
-        *s_dmax = dmax;
-        // last block to finish publishes the iteration's decision: re-select iff any spread exceeds the slack
-        // (every block has read the previous decision before it gets here)
-        int* ctl = reinterpret_cast<int*>(drift + 2 * gridDim.x);
-        __threadfence();
-        if (atomicAdd(ctl + 1, 1) == (int)gridDim.x - 1) {
-            __threadfence();
-            int resel = 0;
-            for (int i = 0; i < (int)gridDim.x; ++i) {
-                const double sp = reinterpret_cast<volatile double*>(drift)[2 * i + 1];
-                if (!(sp <= slack)) resel = 1;   // also NaN
-            }
-            ctl[0] = resel;
-            ctl[1] = 0;
-        }
+        const double spread = dmax - dmin;
+        st.drift[2 * m] = dmax;
+        st.drift[2 * m + 1] = spread;
+        s_red[16] = dmax;
+        if (u == 0u || !(spread <= st.slack)) atomicMax(st.dec + 2 + 2 * h + (u & 1u), u + 1u);     // also NaN
     }
     __syncthreads();
-    // per-column factor of the list pass: 2^(dlu - max dlu) in (0, 1]
-    const double dm = *s_dmax;
+    const double dm = s_red[16];
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const int64_t i = (int64_t)m * K + k;
-        U[i] = exp2(lu[i] - lu_build[i] - dm);
+        __stcg(st.U + i, exp2(__ldcg(st.lu + i) - __ldcg(st.lu_build + i) - dm));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();          // (cumulative: the block's writes above are ordered before the barrier)
+        atomicAdd(st.dec + h, 1u);
+    }
+}
+
+// ---- step-wise kernels (ranks exchange P between reduce and update through the caller's all-reduce) ----------
+__global__ void __launch_bounds__(256)
+sinkhorn_reduce_kernel(const double* __restrict__ partial, SkPart pa, SkPart pb, int K, double* __restrict__ P) {
+    __shared__ int s_off[SK_RED_LIST];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int m = blockIdx.x;
+    sk_reduce_m(m, partial, m < pb.m0 ? pa : pb, K, P, s_off);      // (one range: pa == pb, m0 == 0)
+}
+
+__global__ void __launch_bounds__(256)
+sinkhorn_update_kernel(SkState st, int K, int check_mass, int sparse, int m_half1, unsigned int u,
+                       int32_t* __restrict__ flags) {
+    __shared__ double s_red[18];
+    pdl_wait();
+    pdl_launch_dependents();
+    sk_update_m(blockIdx.x, st, K, check_mass, sparse, (int)blockIdx.x >= m_half1 ? 1 : 0, u, flags, s_red);
+}
+
+// one sparse pass over the table / the lists: per segment the selection or the list pass, as dec[m] says
+__global__ void __launch_bounds__(SK_THREADS, LOOP_CTAS_PER_SM)
+sinkhorn_step_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2, SkPart2 part,
+                     SkState st, unsigned int it, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char lp_smem[];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    SkRings rg = {0u, 0u, 0u, 0u};
+    if (lane == 0) {
+        const uint32_t lb = smem_u32(lp_smem + LOOP_OFF_LBAR) + warp * LP_DEPTH * 8;
+        const uint32_t sb = smem_u32(lp_smem + LOOP_OFF_SBAR) + warp * SK_DEPTH * 8;
+        for (int d = 0; d < LP_DEPTH; ++d) mbar_init(lb + 8 * d, 1);
+        for (int d = 0; d < SK_DEPTH; ++d) mbar_init(sb + 8 * d, 1);
+    }
+    fence_barrier_init();
+    __syncthreads();
+    int bad = 0;
+    for (int h = 0; h < 2; ++h) {
+        const SkPart& ph = part.h[h];
+        const int64_t t_lo = sk_lo(ph, g), t_hi = sk_lo(ph, g + 1);
+        if (t_lo >= t_hi) continue;
+        const int ml_first = (int)(t_lo / ph.tpm);
+        const bool resel = sk_pass_selects(st, h, it);
+        int64_t t = t_lo;
+        while (t < t_hi) {
+            const int ml = (int)(t / ph.tpm), m = ph.m0 + ml;
+            const int64_t t_end = min(t_hi, (int64_t)(ml + 1) * ph.tpm);
+            const int64_t tile0 = t - (int64_t)ml * ph.tpm, tile1 = t_end - (int64_t)ml * ph.tpm;
+            double* dst = st.partial + ((int64_t)g * ph.slots + ph.slot0 + (ml - ml_first)) * SP_K;
+            if (threadIdx.x == 0) atomicAdd(st.abort_w + (resel ? 1 : 2), 1u);
+            if (resel) sk_select_segment(table, B, rBg, scale2, ph.tpm, st, m, tile0, tile1, lp_smem, rg, dst, bad);
+            else sk_list_segment(B, rBg, ph.tpm, st, m, tile0, tile1, lp_smem, rg, dst, bad);
+            t = t_end;
+        }
     }
     if (bad) atomicOr(flags, bad);
 }
 
-__global__ void __launch_bounds__(256)
-sinkhorn_update_kernel(double* __restrict__ lu, const double* __restrict__ P, const double* __restrict__ lu_build,
-                       int K, double Kd, int check_mass, double slack, double* __restrict__ drift,
-                       double* __restrict__ U, int32_t* __restrict__ flags) {
-    __shared__ double red_mx[8], red_mn[8];
-    __shared__ double s_dmax;
-    pdl_wait();
-    pdl_launch_dependents();
-    sk_update_block(lu, P, lu_build, K, Kd, check_mass, slack, drift, U, flags, red_mx, red_mn, &s_dmax);
+// ---- the persistent kernel: the whole iteration loop of one assignment in ONE launch -------------------------
+// Grid = LOOP_CTAS_PER_SM x SMs co-resident CTAs (cooperative launch), the static partition of the step-wise
+// kernels.  For every pass `it` and every segment (sub-vector m) of its range a CTA
+//   waits until the row scaling of m for this pass is published (dec[m], acquire),
+//   runs the selection or the list pass on the segment and writes its row-sum partial,
+//   arrives on m's counter; the LAST CTA to arrive on m reduces the partials of m in CTA order, exchanges the
+//   256 sums with the peer ranks (W > 1: publish in the symmetric buffer, raise a flag per peer with a
+//   system-scope release store, wait for the W flags, sum the W vectors in rank order straight from peer
+//   memory over NVLink -- the reference's `dist.all_reduce(sum_of_rows)`, modeling_repconc.py:156-157, fused
+//   into the pass that produces the sums), updates lu / drift / U / the decision of m and publishes it.
+// Dependencies are per sub-vector, so the reduction + exchange + update of one sub-vector overlap the passes of
+// the others, and nothing ever returns to the host between iterations (the step-wise sequence costs three
+// launches and, between ranks, one collective per iteration).  No deadlock: every CTA executes its (pass,
+// segment) items in lexicographic order and a wait only ever targets an item that precedes the waiter's own.
+// Every spin is bounded (globaltimer): on expiry RC_FLAG_PEER_TIMEOUT is raised and all CTAs leave.
+constexpr int PEERX_MAX_W = 16;
+struct SkPeer {
+    unsigned char* base[PEERX_MAX_W];   // rank p's symmetric buffer as mapped into this process
+    int rank, W;
+    uint32_t seq_base;                  // exchange u of this call carries sequence number seq_base + u + 1
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64x(const double* p) {
+    double v;
+    asm("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__host__ __device__ constexpr size_t sk_peer_header_bytes(int M) { return (size_t)2 * M * PEERX_MAX_W * 4; }
+
+// reduce + (exchange) + update of sub-vector m by one block; u = index of the update (0 = after BEGIN)
+template <int W_T>
+__device__ __forceinline__ bool sk_reduce_update_m(int m, unsigned int u, const SkPart& part, const SkState& st, int M,
+                                                   int32_t* __restrict__ flags, const SkPeer& peer,
+                                                   unsigned char* smem) {
+    int* s_off = reinterpret_cast<int*>(smem + LOOP_OFF_RED);          // the reduction scratch is free here
+    double* s_red = reinterpret_cast<double*>(smem + LOOP_OFF_MISC);
+    int* s_flag = reinterpret_cast<int*>(smem + LOOP_OFF_MISC + 18 * 8);
+    sk_reduce_m(m, st.partial, part, SP_K, st.P, s_off);
+    if (W_T != 1) {
+        const int W = W_T > 0 ? W_T : peer.W;
+        const uint32_t seq = peer.seq_base + u + 1u;
+        const size_t par = seq & 1u;
+        const size_t hdr = sk_peer_header_bytes(M);
+        const size_t voff = (par * M + m) * SP_K;
+        const size_t fidx = (par * M + m) * PEERX_MAX_W;
+        // 1. publish this rank's 256 sums (each thread re-reads the value it stored itself)
+        reinterpret_cast<double*>(peer.base[peer.rank] + hdr)[voff + threadIdx.x] =
+            __ldcg(st.P + (int64_t)m * SP_K + threadIdx.x);
+        __threadfence_system();
+        if (threadIdx.x == 0) *s_flag = 0;
+        __syncthreads();
+        // 2. signal every peer, 3. wait for every peer
+        if ((int)threadIdx.x < W) {
+            st_release_sys_u32(reinterpret_cast<uint32_t*>(peer.base[threadIdx.x]) + fidx + peer.rank, seq);
+            const uint32_t* my = reinterpret_cast<const uint32_t*>(peer.base[peer.rank]) + fidx + threadIdx.x;
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while ((int32_t)(ld_acquire_sys_u32(my) - seq) < 0) {        // sequence numbers only grow (wrap-safe)
+                if ((++spins & 255u) == 0u &&
+                    (global_timer_ns() - t0 > peer.timeout_ns || *reinterpret_cast<volatile unsigned int*>(st.abort_w))) {
+                    *s_flag = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (*s_flag) {
+            if (threadIdx.x == 0) {
+                atomicOr(flags, RC_FLAG_PEER_TIMEOUT);
+                atomicExch(st.abort_w, 1u);
+            }
+            return false;
+        }
+        // 4. sum in rank order straight from peer memory: every rank holds the bitwise identical result
+        double v[PEERX_MAX_W];
+#pragma unroll
+        for (int p = 0; p < PEERX_MAX_W; ++p)
+            if (p < W) v[p] = ld_relaxed_sys_f64x(reinterpret_cast<const double*>(peer.base[p] + hdr) + voff + threadIdx.x);
+        double sum = 0.0;
+#pragma unroll
+        for (int p = 0; p < PEERX_MAX_W; ++p)
+            if (p < W) sum += v[p];
+        __stcg(st.P + (int64_t)m * SP_K + threadIdx.x, sum);
+    }
+    __syncthreads();
+    sk_update_m(m, st, SP_K, u > 0 ? 1 : 0, 1, m >= M / 2 ? 1 : 0, u, flags, s_red);
+    return true;
 }
 
-// reduce + update in one launch: the single-rank solve (rc_sinkhorn_solve) has no all-reduce between them.
-// Same arithmetic, same order as the two kernels above.
-__global__ void __launch_bounds__(256)
-sinkhorn_reduce_update_kernel(const double* __restrict__ partial, SkPart part_in, SkPart part_list, int K, int csr_mode,
-                              int M, int force, int check_mass, SkState st, int32_t* __restrict__ flags) {
-    __shared__ int s_off[SK_RED_LIST];
-    __shared__ double red_mx[8], red_mn[8];
-    __shared__ double s_dmax;
-    pdl_wait();
-    pdl_launch_dependents();
-    sk_reduce_block(partial, part_in, part_list, K, st.P, csr_mode, M, force, st, s_off);
-    __syncthreads();   // P[m,:] and lu_build[m,:] of this block are final (each element is re-read by its writer)
-    sk_update_block(st.lu, st.P, st.lu_build, K, (double)K, check_mass, st.slack, st.drift, st.U, flags, red_mx,
-                    red_mn, &s_dmax);
+template <int W_T>
+__global__ void __launch_bounds__(SK_THREADS, LOOP_CTAS_PER_SM)
+sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2, SkPart part_begin,
+                     SkPart2 part, SkState st, int n_pass, int32_t* __restrict__ flags, SkPeer peer) {
+    extern __shared__ __align__(128) unsigned char lp_smem[];
+    int* s_ctl = reinterpret_cast<int*>(lp_smem + LOOP_OFF_MISC + 18 * 8 + 8);   // {decision word, last, abort}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    // the row scaling after BEGIN (update 0; BEGIN's partials follow its own single-range partition), dealt out
+    // over the CTAs
+    for (int m = g; m < M; m += gridDim.x)
+        if (!sk_reduce_update_m<W_T>(m, 0u, part_begin, st, M, flags, peer, lp_smem)) return;
+    if (n_pass <= 0) return;
+    SkRings rg = {0u, 0u, 0u, 0u};
+    if (lane == 0) {
+        const uint32_t lb = smem_u32(lp_smem + LOOP_OFF_LBAR) + warp * LP_DEPTH * 8;
+        const uint32_t sb = smem_u32(lp_smem + LOOP_OFF_SBAR) + warp * SK_DEPTH * 8;
+        for (int d = 0; d < LP_DEPTH; ++d) mbar_init(lb + 8 * d, 1);
+        for (int d = 0; d < SK_DEPTH; ++d) mbar_init(sb + 8 * d, 1);
+    }
+    fence_barrier_init();
+    __syncthreads();
+    int bad = 0;
+    // time spent waiting / selecting / iterating on lists / arriving + reducing + updating, summed over CTAs
+    // (thread 0's clock; diagnostics read back through rc_sinkhorn_list_stats)
+    unsigned long long prof[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned long long tp = global_timer_ns();
+    auto lap = [&](int what) {
+        if (threadIdx.x == 0) {
+            const unsigned long long now = global_timer_ns();
+            prof[what] += now - tp;
+            tp = now;
+        }
+    };
+    for (int it = 0; it < n_pass; ++it) {
+        for (int h = 0; h < 2; ++h) {
+            const SkPart& ph = part.h[h];
+            const int64_t t_lo = sk_lo(ph, g), t_hi = sk_lo(ph, g + 1);
+            if (t_lo >= t_hi) continue;
+            const int ml_first = (int)(t_lo / ph.tpm);
+            // pass `it` on this half may start once update `it` of ALL its sub-vectors is in place; they were
+            // released while this CTA worked on the other half
+            if (threadIdx.x == 0) {
+                const unsigned int want = (unsigned int)(it + 1) * (unsigned int)(ph.total / ph.tpm);
+                const unsigned long long t0 = global_timer_ns();
+                unsigned int spins = 0;
+                int ab = 0;
+                // (pass 0 overwrites partial rows that BEGIN laid out differently: every initial update, of either
+                //  half, must have consumed them)
+                const unsigned int want_other = it == 0 ? (unsigned int)(part.h[1 - h].total / ph.tpm) : 0u;
+                while (ld_acquire_gpu_u32(st.dec + h) < want || ld_acquire_gpu_u32(st.dec + 1 - h) < want_other) {
+                    if ((++spins & 255u) == 0u) {
+                        if (*reinterpret_cast<volatile unsigned int*>(st.abort_w)) { ab = 1; break; }
+                        if (global_timer_ns() - t0 > peer.timeout_ns) {
+                            atomicOr(flags, RC_FLAG_PEER_TIMEOUT);
+                            atomicExch(st.abort_w, 1u);
+                            ab = 1;
+                            break;
+                        }
+                    }
+                }
+                s_ctl[0] = sk_pass_selects(st, h, (unsigned int)it) ? 1 : 0;
+                s_ctl[2] = ab;
+            }
+            __syncthreads();
+            if (s_ctl[2]) {
+                if (bad) atomicOr(flags, bad);
+                return;
+            }
+            const bool resel = s_ctl[0] != 0;
+            lap(0);
+            int64_t t = t_lo;
+            while (t < t_hi) {
+                const int ml = (int)(t / ph.tpm), m = ph.m0 + ml;
+                const int64_t t_end = min(t_hi, (int64_t)(ml + 1) * ph.tpm);
+                const int64_t tile0 = t - (int64_t)ml * ph.tpm, tile1 = t_end - (int64_t)ml * ph.tpm;
+                if (threadIdx.x == 0) atomicAdd(st.abort_w + (resel ? 1 : 2), 1u);
+
+                double* dst = st.partial + ((int64_t)g * ph.slots + ph.slot0 + (ml - ml_first)) * SP_K;
+                if (resel) sk_select_segment(table, B, rBg, scale2, ph.tpm, st, m, tile0, tile1, lp_smem, rg, dst, bad);
+                else sk_list_segment(B, rBg, ph.tpm, st, m, tile0, tile1, lp_smem, rg, dst, bad);
+                lap(resel ? 1 : 2);
+                // arrive on m (the pass functions end with a block barrier after the partial is written: thread 0's
+                // fence + atomic publishes the whole block's writes); the last CTA does the reduction, the exchange
+                // and the update that opens the next pass on m
+                if (bad) {
+                    atomicOr(flags, bad);
+                    bad = 0;
+                }
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    const unsigned int prev = atomicAdd(st.arrive + m, 1u);
+                    const int last = prev + 1u == (unsigned int)sk_ctas_of_m(ph, m);
+                    if (last) {
+                        st.arrive[m] = 0u;          // nobody touches the counter again before the update below is published
+                        __threadfence();
+                    }
+                    s_ctl[1] = last;
+                }
+                __syncthreads();
+                if (s_ctl[1]) {
+                    if (!sk_reduce_update_m<W_T>(m, (unsigned int)(it + 1), ph, st, M, flags, peer, lp_smem)) return;
+                }
+                lap(3);
+                t = t_end;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) st.cta_ns[4 * g + i] = prof[i];
+    }
 }
 
 // Transport plan Q (M,K,B) fp64 from the row scaling alone (API parity with sinkhorn_algorithm's return
@@ -1386,8 +1609,10 @@ sinkhorn_expand_kernel(const float* __restrict__ table, int64_t B, int M, int K,
         Q[((int64_t)m * K + k) * B + b] = exp2(fma(-(double)row[k], scale2, lu[k]) - mx) / s;
 }
 
-__global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t pairs, unsigned long long* out) {
+__global__ void list_stats_kernel(const uint2* __restrict__ csr, int64_t pairs, unsigned long long* out,
+                                  const unsigned int* __restrict__ counters) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4) out[36 + i] = counters[1 + i];
     if (i >= pairs) return;
     const uint32_t cc = csr[i].y;
 #pragma unroll
@@ -1466,42 +1691,92 @@ static int launch_pass(float* table, const float* minmax, int64_t B, double Bg, 
     return RC_OK;
 }
 
-static int launch_reduce(const SkPart& p, const SkState& s, int M, int K, cudaStream_t st, int csr_mode = 0,
-                         int force = 0, const SkPart* p_list = nullptr) {
-    RC_CUDA(launch_chain(sinkhorn_reduce_kernel, (unsigned)M, 256u, 0, st, s.partial, p, p_list ? *p_list : p, K, s.P,
-                         csr_mode, M, force, s));
+// pa / pb: the partition the pass that wrote the partials worked with (one range: pa == pb; the sparse passes: the
+// two halves)
+static int launch_reduce(const SkPart& pa, const SkPart& pb, const SkState& s, int M, int K, cudaStream_t st) {
+    RC_CUDA(launch_chain(sinkhorn_reduce_kernel, (unsigned)M, 256u, 0, st, (const double*)s.partial, pa, pb, K, s.P));
     RC_CHECK_LAUNCH("sinkhorn_reduce_kernel");
     return RC_OK;
 }
 
-static int launch_update(const SkState& s, int M, int K, double Bg, int check_mass, int32_t* flags,
-                         cudaStream_t st) {
-    (void)Bg;
-    RC_CUDA(launch_chain(sinkhorn_update_kernel, (unsigned)M, 256u, 0, st, s.lu, s.P, s.lu_build, K, (double)K, check_mass,
-                         s.slack, s.drift, s.U, flags));
+// update u: u = 0 follows BEGIN (its row sums are those of the unnormalised Q0: no mass check, and the first
+// sparse pass always selects)
+static int launch_update(const SkState& s, int M, int K, int sparse, unsigned int u, int32_t* flags, cudaStream_t st) {
+    RC_CUDA(launch_chain(sinkhorn_update_kernel, (unsigned)M, 256u, 0, st, s, K, (sparse && u > 0) ? 1 : 0, sparse,
+                         M / 2, u, flags));
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
 }
 
-// One sparse iteration (K == 256): the selection pass and the list pass are both launched; exactly one of them
-// works (device-side decision from the drift the update kernel just wrote; force = 1: select).
-static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, int M, double eps, int force,
-                              const SkState& s, int32_t* flags, cudaStream_t st, SkPart* ps_out, SkPart* pl_out) {
+static int loop_smem_attr() {
     static unsigned long long attr_seen = 0ull;
     if (first_use_on_device(attr_seen)) {
-        RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-        RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_loop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_loop_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
+        RC_CUDA(cudaFuncSetAttribute(sinkhorn_loop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOP_SMEM));
     }
-    const SkPart ps = sk_partition(B, M, SP_CTAS_PER_SM), pl = sk_partition(B, M, LP_CTAS_PER_SM);
+    return RC_OK;
+}
+
+// One sparse pass (K == 256) as its own launch: per segment the selection or the list pass, as dec[m] says.
+static int launch_sparse_step(const float* table, int64_t B, int64_t B_global, int M, double eps, const SkPart2& p2,
+                              const SkState& s, unsigned int it, int32_t* flags, cudaStream_t st) {
+    int rc = loop_smem_attr();
+    if (rc) return rc;
     const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
-    RC_CUDA(launch_chain(sinkhorn_step_sparse_kernel, ps.G, SK_THREADS, SP_SMEM, st, table, B, rBg, M, scale2, ps, s.lu,
-                         s.drift, force, s, s.partial, flags));
-    RC_CHECK_LAUNCH("sinkhorn_step_sparse_kernel");
-    RC_CUDA(launch_chain(sinkhorn_step_list_kernel, pl.G, SK_THREADS, LP_SMEM, st, B, rBg, M, pl, s.drift, force, s,
-                         s.partial, flags));
-    RC_CHECK_LAUNCH("sinkhorn_step_list_kernel");
-    *ps_out = ps;
-    *pl_out = pl;
+    RC_CUDA(launch_chain(sinkhorn_step_kernel, (unsigned)p2.h[1].G, (unsigned)SK_THREADS, (size_t)LOOP_SMEM, st, table, B,
+                         rBg, M, scale2, p2, s, it, flags));
+    RC_CHECK_LAUNCH("sinkhorn_step_kernel");
+    return RC_OK;
+}
+
+static unsigned long long peer_timeout_ns() {
+    static unsigned long long v = 0;
+    if (v == 0) {
+        const char* e = getenv("RC_PEER_TIMEOUT_MS");
+        double ms = (e && e[0]) ? atof(e) : 30000.0;      // a stalled host on one rank (GC, checkpoint) must not kill training
+        if (!(ms >= 1.0)) ms = 30000.0;
+        v = (unsigned long long)(ms * 1e6);
+    }
+    return v;
+}
+
+// The whole iteration loop in one cooperative launch (see sinkhorn_loop_kernel).  Returns RC_E_UNSUPPORTED when the
+// grid cannot be co-resident (the caller then runs the step-wise sequence).
+static int launch_loop(const float* table, int64_t B, int64_t B_global, int M, double eps, int n_pass, const SkPart& p,
+                       const SkPart2& p2, const SkState& s, int32_t* flags, const SkPeer& peer, cudaStream_t st) {
+    int rc = loop_smem_attr();
+    if (rc) return rc;
+    void (*kern)(const float*, int64_t, double, int, double, SkPart, SkPart2, SkState, int, int32_t*, SkPeer);
+    switch (peer.W) {
+        case 1: kern = sinkhorn_loop_kernel<1>; break;
+        case 2: kern = sinkhorn_loop_kernel<2>; break;
+        case 4: kern = sinkhorn_loop_kernel<4>; break;
+        case 8: kern = sinkhorn_loop_kernel<8>; break;
+        default: kern = sinkhorn_loop_kernel<0>; break;
+    }
+    int per_sm = 0;
+    RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, (size_t)LOOP_SMEM));
+    if (per_sm * num_sms() < p2.h[1].G) {
+        set_error("sinkhorn loop: %d CTAs cannot be co-resident (%d per SM)", p2.h[1].G, per_sm);
+        return RC_E_UNSUPPORTED;
+    }
+    const double rBg = 1.0 / (double)B_global, scale2 = RC_LOG2E / eps;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p2.h[1].G);
+    cfg.blockDim = dim3((unsigned)SK_THREADS);
+    cfg.dynamicSmemBytes = (size_t)LOOP_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of the whole grid is what the spins rely on
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, table, B, rBg, M, scale2, p, p2, s, n_pass, flags, peer));
+    RC_CHECK_LAUNCH("sinkhorn_loop_kernel");
     return RC_OK;
 }
 
@@ -1612,15 +1887,12 @@ RC_API int rc_dist_table(const float* x, int64_t ldx, const float* centroids, in
 }
 
 static int sk_reset(const SkState& s, int64_t B, int M, int K, cudaStream_t st) {
-    const int64_t n = (int64_t)M * K;
+    const size_t n = (size_t)M * K * 8;
     if (K == SP_K)   // pair directory: entries of rows past B stay empty
         RC_CUDA(cudaMemsetAsync(s.csr, 0, (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS * sizeof(uint2), st));
-    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu, n, 0.0);
-    RC_CHECK_LAUNCH("fill_f64_kernel");
-    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.lu_build, n, 0.0);
-    RC_CHECK_LAUNCH("fill_f64_kernel");
-    RC_CUDA(cudaMemsetAsync(s.drift + 2 * M, 0, 16, st));
-    RC_CUDA(cudaMemsetAsync(s.cursor, 0, 8, st));
+    RC_CUDA(cudaMemsetAsync(s.lu, 0, n, st));              // +0.0
+    RC_CUDA(cudaMemsetAsync(s.lu_build, 0, n, st));
+    RC_CUDA(cudaMemsetAsync(s.cursor, 0, (size_t)M * 16 + 64 + 32, st));   // done / trig, arrival counters, abort, diagnostics
     return RC_OK;
 }
 
@@ -1659,57 +1931,97 @@ RC_API int rc_sinkhorn_begin(float* table, const float* minmax, int64_t B, int M
     if (rc) return rc;
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
-    return launch_reduce(p, s, M, K, st);
+    return launch_reduce(p, p, s, M, K, st);
 }
 
-/* Single-rank solve: rc_sinkhorn_begin + (iters - 1) x rc_sinkhorn_step + rc_sinkhorn_finish in one call.  With no
- * all-reduce between the row-sum reduction and the row normalisation the two run as ONE kernel per iteration
- * (sinkhorn_reduce_update_kernel); everything else is the kernels of the step-wise entry points in the same
- * order, so the results are bit-identical to the step-wise sequence with B_global == B. */
-RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
-                             int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
-                             void* stream) {
+// Sinkhorn + argmax of one assignment in one call.  Sparse passes (K == 256, dense == 0): BEGIN, ONE persistent
+// kernel for the whole iteration loop (with the row sums exchanged over peer memory inside it when W > 1), FINISH.
+// Otherwise (any K, or the dense re-run) and W == 1: the kernels of the step-wise entry points back to back.
+static int sinkhorn_solve_impl(float* table, const float* minmax, int64_t B, int64_t B_global, int M, int K, double eps,
+                               int iters, int dense, void* state, const SkPeer& peer, int64_t* codes_mb,
+                               uint8_t* codes_u8, int32_t* flags, cudaStream_t st) {
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(minmax, "rc_sinkhorn_solve: null minmax");
     RC_REQUIRE(iters >= 0, "rc_sinkhorn_solve: iters < 0");
+    RC_REQUIRE(B_global >= B, "rc_sinkhorn_solve: B_global < B");
     RC_REQUIRE(codes_mb || codes_u8, "rc_sinkhorn_solve: no output");
     RC_REQUIRE(!codes_u8 || K <= 256, "rc_sinkhorn_solve: uint8 codes need K <= 256");
-    cudaStream_t st = (cudaStream_t)stream;
     const SkPart p = sk_partition(B, M);
+    const SkPart2 p2 = sk_partition2(B, M, LOOP_CTAS_PER_SM);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
+    const bool sparse = sk_use_sparse(table, K, dense);
+    if (peer.W > 1 && !sparse) {
+        set_error("rc_sinkhorn_solve_peer: the fused exchange exists for the sparse passes (K == 256, dense == 0) only");
+        return RC_E_UNSUPPORTED;
+    }
     rc = sk_reset(s, B, M, K, st);
     if (rc) return rc;
     rc = launch_pass<SK_BEGIN>(table, minmax, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
     if (rc) return rc;
-    if (iters >= 1 && B == 1) {
+    if (iters >= 1 && B_global == 1) {
         // one column: every entry is exactly 1/K after the row normalisation (see rc_sinkhorn_finish)
         if (codes_mb) RC_CUDA(cudaMemsetAsync(codes_mb, 0, (size_t)M * B * sizeof(int64_t), st));
         if (codes_u8) RC_CUDA(cudaMemsetAsync(codes_u8, 0, (size_t)M * B, st));
         return RC_OK;
     }
-    const bool sparse = sk_use_sparse(table, K, dense);
-    // which pass wrote the partials the next reduce+update consumes
-    int csr_mode = 0, force = 0;
-    SkPart pin = p, plist = p;
-    for (int it = 0; it < iters; ++it) {
-        const bool last = it == iters - 1;
-        RC_CUDA(launch_chain(sinkhorn_reduce_update_kernel, (unsigned)M, 256u, 0, st, s.partial, pin, plist, K, csr_mode,
-                             M, force, (sparse && it > 0) ? 1 : 0, s, flags));
-        RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
-        if (last) break;
+    if (iters >= 1) {
+        bool looped = false;
         if (sparse) {
-            force = it == 0 ? 1 : 0;
-            rc = launch_sparse_step(table, B, B, M, eps, force, s, flags, st, &pin, &plist);
-            if (rc) return rc;
-            csr_mode = 1;
-        } else {
-            rc = launch_pass<SK_STEP>(table, nullptr, B, (double)B, M, K, eps, p, s, nullptr, nullptr, flags, st);
-            if (rc) return rc;
+            rc = launch_loop(table, B, B_global, M, eps, iters - 1, p, p2, s, flags, peer, st);
+            if (rc == RC_OK) looped = true;
+            else if (rc != RC_E_UNSUPPORTED || peer.W > 1) return rc;
+        }
+        if (!looped) {
+            for (int it = 0; it < iters; ++it) {
+                rc = (sparse && it > 0) ? launch_reduce(p2.h[0], p2.h[1], s, M, K, st) : launch_reduce(p, p, s, M, K, st);
+                if (rc) return rc;
+                rc = launch_update(s, M, K, sparse ? 1 : 0, (unsigned int)it, flags, st);
+                if (rc) return rc;
+                if (it == iters - 1) break;
+                if (sparse) rc = launch_sparse_step(table, B, B_global, M, eps, p2, s, (unsigned int)it, flags, st);
+                else rc = launch_pass<SK_STEP>(table, nullptr, B, (double)B_global, M, K, eps, p, s, nullptr, nullptr, flags, st);
+                if (rc) return rc;
+            }
         }
     }
     return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, dense, st);
+}
+
+RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
+                             int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
+                             void* stream) {
+    SkPeer peer{};
+    peer.W = 1;
+    peer.timeout_ns = peer_timeout_ns();
+    return sinkhorn_solve_impl(table, minmax, B, B, M, K, eps, iters, dense, state, peer, codes_mb, codes_u8, flags,
+                               (cudaStream_t)stream);
+}
+
+RC_API size_t rc_sinkhorn_peer_buffer_bytes(int M, int K) {
+    if (M < 1 || K < 1) return 0;
+    return sk_peer_header_bytes(M) + (size_t)2 * M * K * 8;
+}
+
+RC_API int rc_sinkhorn_solve_peer(float* table, const float* minmax, int64_t B, int64_t B_global, int M, int K,
+                                  double eps, int iters, void* state, const uint64_t* peer_buffers_host, int rank,
+                                  int W, uint32_t seq_base, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
+                                  void* stream) {
+    RC_REQUIRE(peer_buffers_host, "rc_sinkhorn_solve_peer: null peer buffers");
+    RC_REQUIRE(W >= 1 && W <= PEERX_MAX_W && rank >= 0 && rank < W, "rc_sinkhorn_solve_peer: bad rank %d / world %d", rank, W);
+    RC_REQUIRE(K == SP_K, "rc_sinkhorn_solve_peer: K must be 256 (K=%d)", K);
+    SkPeer peer{};
+    for (int p = 0; p < W; ++p) {
+        RC_REQUIRE(peer_buffers_host[p] != 0, "rc_sinkhorn_solve_peer: null peer buffer %d", p);
+        peer.base[p] = reinterpret_cast<unsigned char*>(peer_buffers_host[p]);
+    }
+    peer.rank = rank;
+    peer.W = W;
+    peer.seq_base = seq_base;
+    peer.timeout_ns = peer_timeout_ns();
+    return sinkhorn_solve_impl(table, minmax, B, B_global, M, K, eps, iters, 0, state, peer, codes_mb, codes_u8, flags,
+                               (cudaStream_t)stream);
 }
 
 RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int M, int K, double eps,
@@ -1717,27 +2029,38 @@ RC_API int rc_sinkhorn_step(const float* table, int64_t B, int64_t B_global, int
     int rc = sk_args(table, B, M, K, eps, state, flags);
     if (rc) return rc;
     RC_REQUIRE(B_global >= B, "rc_sinkhorn_step: B_global < B");
+    RC_REQUIRE(step_index >= 0, "rc_sinkhorn_step: step_index < 0");
     cudaStream_t st = (cudaStream_t)stream;
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
     // The sparse pass needs rows (centroids) that kept their share of the mass through the previous column
-    // normalisation; the update kernel checks that from the second STEP on (the first update sees the row
-    // sums of the unnormalised Q0, which say nothing about it).
+    // normalisation; the update checks that from the second STEP on (the first update sees the row sums of the
+    // unnormalised Q0, which say nothing about it).
     const bool sparse = sk_use_sparse(table, K, dense);
-    rc = launch_update(s, M, K, (double)B_global, (sparse && step_index > 0) ? 1 : 0, flags, st);
+    rc = launch_update(s, M, K, sparse ? 1 : 0, (unsigned int)step_index, flags, st);
     if (rc) return rc;
     if (sparse) {
-        const int force = step_index == 0 ? 1 : 0;
-        SkPart ps, pl;
-        rc = launch_sparse_step(table, B, B_global, M, eps, force, s, flags, st, &ps, &pl);
+        const SkPart2 p2 = sk_partition2(B, M, LOOP_CTAS_PER_SM);
+        rc = launch_sparse_step(table, B, B_global, M, eps, p2, s, (unsigned int)step_index, flags, st);
         if (rc) return rc;
-        return launch_reduce(ps, s, M, K, st, 1, force, &pl);
+        return launch_reduce(p2.h[0], p2.h[1], s, M, K, st);
     }
-    rc = launch_pass<SK_STEP>(const_cast<float*>(table), nullptr, B, (double)B_global, M, K, eps, p, s, nullptr,
-                              nullptr, flags, st);
+    rc = launch_pass<SK_STEP>(const_cast<float*>(table), nullptr, B, (double)B_global, M, K, eps, p, s, nullptr, nullptr,
+                              flags, st);
     if (rc) return rc;
-    return launch_reduce(p, s, M, K, st);
+    return launch_reduce(p, p, s, M, K, st);
+}
+
+RC_API int rc_sinkhorn_debug_cta_times(void* state, int64_t B, int M, int K, int64_t* out_host, int max_ctas) {
+    RC_REQUIRE(state && out_host && B >= 1 && M >= 1 && K >= 1, "rc_sinkhorn_debug_cta_times: bad argument");
+    const SkPart p = sk_partition(B, M);
+    SkState s;
+    sk_layout(B, M, K, p, state, &s);
+    const int G = std::min(max_ctas, num_sms() * LOOP_CTAS_PER_SM);
+    RC_CUDA(cudaDeviceSynchronize());
+    RC_CUDA(cudaMemcpy(out_host, s.cta_ns, (size_t)G * 4 * 8, cudaMemcpyDeviceToHost));
+    return G;
 }
 
 RC_API int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream) {
@@ -1747,9 +2070,9 @@ RC_API int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t*
     const SkPart p = sk_partition(B, M);
     SkState s;
     sk_layout(B, M, K, p, state, &s);
-    RC_CUDA(cudaMemsetAsync(out, 0, 36 * sizeof(int64_t), st));
+    RC_CUDA(cudaMemsetAsync(out, 0, 40 * sizeof(int64_t), st));
     const int64_t pairs = (int64_t)M * p.tpm * SK_WARPS;
-    list_stats_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(s.csr, pairs, (unsigned long long*)out);
+    list_stats_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(s.csr, pairs, (unsigned long long*)out, s.abort_w);
     RC_CHECK_LAUNCH("list_stats_kernel");
     return RC_OK;
 }
@@ -1764,7 +2087,7 @@ RC_API int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, i
     SkState s;
     sk_layout(B, M, K, p, state, &s);
     if (apply_rowsum) {
-        rc = launch_update(s, M, K, (double)B_global, 0, flags, st);
+        rc = launch_update(s, M, K, 0, 0u, flags, st);
         if (rc) return rc;
     }
     dim3 grid((unsigned)((B + 7) / 8), (unsigned)M);
@@ -1794,8 +2117,8 @@ RC_API int rc_sinkhorn_finish(const float* table, int64_t B, int64_t B_global, i
     if (apply_rowsum) {
         // the row sums of the last sparse pass get the same mass check as every other one (steps_done >= 1: they
         // come from a STEP pass, not from BEGIN's unnormalised Q0 -- see rc_sinkhorn_step)
-        const int check = (sk_use_sparse(table, K, dense) && steps_done >= 1) ? 1 : 0;
-        rc = launch_update(s, M, K, (double)B_global, check, flags, st);
+        rc = launch_update(s, M, K, sk_use_sparse(table, K, dense) ? 1 : 0, (unsigned int)(steps_done > 0 ? steps_done : 0),
+                           flags, st);
         if (rc) return rc;
     }
     return launch_finish(table, B, M, K, eps, p, s, codes_mb, codes_u8, flags, dense, st);

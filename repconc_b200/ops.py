@@ -153,6 +153,30 @@ class CudaAssignKernels:
                                               u8, self.flags.data_ptr(), _stream()), "rc_sinkhorn_solve")
         return out if uint8 else out.t()
 
+    def solve_fused(self, eps, iters, B_global, group=None, uint8=False, dense=False):
+        """W ranks: Sinkhorn + argmax with the per-iteration exchange of the row sums inside the persistent kernel
+        (rc_sinkhorn_solve_peer).  Returns None when that path does not apply (dense re-run, K != 256, no peer
+        memory) -- the caller then runs the step-wise sequence with all-reduces in between.  Needs table() and the
+        all-reduced extrema first."""
+        if dense or self.K != 256 or iters < 1:
+            return None
+        from .peer import PeerSolve
+        ps = PeerSolve.get(self.M, self.K, self.device, group)
+        if ps is None:
+            return None
+        self._alloc_state()
+        if uint8:
+            out = torch.empty((self.B, self.M), dtype=torch.uint8, device=self.device)
+            mb, u8 = None, out.data_ptr()
+        else:
+            out = torch.empty((self.M, self.B), dtype=torch.int64, device=self.device)
+            mb, u8 = out.data_ptr(), None
+        _lib.check(self.lib.rc_sinkhorn_solve_peer(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, int(B_global),
+                                                   self.M, self.K, float(eps), int(iters), self.state.data_ptr(),
+                                                   ps.ptrs, ps.rank, ps.world, ps.take_seq(iters), mb, u8,
+                                                   self.flags.data_ptr(), _stream()), "rc_sinkhorn_solve_peer")
+        return out if uint8 else out.t()
+
     def begin(self, eps):
         self._alloc_state()
         _lib.check(self.lib.rc_sinkhorn_begin(self.tab.data_ptr(), self.minmax.data_ptr(), self.B, self.M, self.K,

@@ -66,3 +66,52 @@ class PeerAllReduce:
                                                   vec.data_ptr(), flags.data_ptr(),
                                                   torch.cuda.current_stream().cuda_stream),
                    "rc_peer_allreduce_f64")
+
+
+class PeerSolve:
+    """Symmetric buffers + sequence counter for rc_sinkhorn_solve_peer (the persistent Sinkhorn kernel with the
+    row-sum exchange fused in).  One instance per (M, K, device, group); None when symmetric memory is unavailable."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, M, K, device, group=None):
+        if os.environ.get("RC_PEER_ALLREDUCE", "1") in ("0", "false", "False"):
+            return None
+        if PeerAllReduce._disabled_reason is not None:
+            return None
+        group = group if group is not None else dist.group.WORLD
+        if dist.get_world_size(group) > 16:
+            return None
+        key = (int(M), int(K), str(device), id(group))
+        inst = cls._cache.get(key)
+        if inst is None:
+            try:
+                inst = cls(int(M), int(K), device, group)
+            except Exception as e:  # symmetric memory not available on this system / build
+                PeerAllReduce._disabled_reason = f"{type(e).__name__}: {e}"
+                logger.warning("repconc_b200: peer exchange unavailable (%s); using NCCL", PeerAllReduce._disabled_reason)
+                return None
+            cls._cache[key] = inst
+        return inst
+
+    def __init__(self, M, K, device, group):
+        import torch.distributed._symmetric_memory as symm
+        lib = _lib.load()
+        self.lib, self.group = lib, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = lib.rc_sinkhorn_peer_buffer_bytes(M, K)
+        with torch.cuda.device(device):
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.hdl = symm.rendezvous(self.buf, group)
+            ptrs = list(self.hdl.buffer_ptrs)
+            assert len(ptrs) == self.world
+            self.ptrs = (ctypes.c_uint64 * self.world)(*ptrs)
+            self.hdl.barrier()          # every rank's flags are zero before the first exchange
+        self.seq = 0
+
+    def take_seq(self, iters):
+        """sequence numbers of one call: returns seq_base and advances by the number of exchanges (iters, min 1)"""
+        base = self.seq
+        self.seq += max(int(iters), 1)
+        return base

@@ -315,7 +315,7 @@ def test_list_pass_oversized_rows():
             k.table()
             out[dense] = (k.solve(0.003, 12).clone(), k.P.clone(), k.read_flags())
             if not dense:
-                st = torch.zeros(36, dtype=torch.int64, device="cuda")
+                st = torch.zeros(44, dtype=torch.int64, device="cuda")
                 from repconc_b200 import _lib
                 _lib.check(k.lib.rc_sinkhorn_list_stats(k.state.data_ptr(), B, M, 256, st.data_ptr(),
                                                         torch.cuda.current_stream().cuda_stream), "stats")
