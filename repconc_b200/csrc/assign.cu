@@ -858,6 +858,8 @@ __device__ __forceinline__ void sk_select_segment(const float* __restrict__ tabl
             if (lane == 0) atomicAdd(st.abort_w + 4, 1u);
         }
         // 3. fp64 evaluation of this lane's survivors, shifted by the row maximum, straight into the record
+        // (staging the record in shared memory and writing it out with coalesced 16-byte vectors was measured:
+        //  no faster -- the pass is not bound by the partial-sector stores)
         const double shift = (double)mx;
         double e[8];
         double s = 0.0;
@@ -1336,7 +1338,22 @@ sinkhorn_update_kernel(SkState st, int K, int check_mass, int sparse, int m_half
     sk_update_m(blockIdx.x, st, K, check_mass, sparse, (int)blockIdx.x >= m_half1 ? 1 : 0, u, flags, s_red);
 }
 
-// one sparse pass over the table / the lists: per segment the selection or the list pass, as dec[m] says
+// reduce + update in one launch: a single rank has no exchange between them.  Same functions, same order as the
+// two kernels above and as the persistent kernel.
+__global__ void __launch_bounds__(256)
+sinkhorn_reduce_update_kernel(SkPart pa, SkPart pb, SkState st, int K, int check_mass, int sparse, int m_half1,
+                              unsigned int u, int32_t* __restrict__ flags) {
+    __shared__ int s_off[SK_RED_LIST];
+    __shared__ double s_red[18];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int m = blockIdx.x;
+    sk_reduce_m(m, st.partial, m < pb.m0 ? pa : pb, K, st.P, s_off);
+    __syncthreads();
+    sk_update_m(m, st, K, check_mass, sparse, m >= m_half1 ? 1 : 0, u, flags, s_red);
+}
+
+// one sparse pass over the table / the lists: per segment the selection or the list pass, as the half's decision says
 __global__ void __launch_bounds__(SK_THREADS, LOOP_CTAS_PER_SM)
 sinkhorn_step_kernel(const float* __restrict__ table, int64_t B, double rBg, int M, double scale2, SkPart2 part,
                      SkState st, unsigned int it, int32_t* __restrict__ flags) {
@@ -1501,11 +1518,16 @@ sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int
     unsigned long long prof[4] = {0ull, 0ull, 0ull, 0ull};
     unsigned long long tp = global_timer_ns();
     auto lap = [&](int what) {
+#ifdef RC_LOOP_PROFILE
         if (threadIdx.x == 0) {
             const unsigned long long now = global_timer_ns();
             prof[what] += now - tp;
             tp = now;
         }
+#else
+        (void)what;
+        (void)tp;
+#endif
     };
     for (int it = 0; it < n_pass; ++it) {
         for (int h = 0; h < 2; ++h) {
@@ -1544,6 +1566,33 @@ sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int
             }
             const bool resel = s_ctl[0] != 0;
             lap(0);
+            int own_m[2], n_own = 0;
+            // wait until every CTA of m has arrived, then reduce + exchange + update m (this CTA arrived first)
+            auto settle = [&](int m) -> bool {
+                if (threadIdx.x == 0) {
+                    const unsigned int n = (unsigned int)sk_ctas_of_m(ph, m);
+                    const unsigned long long t0 = global_timer_ns();
+                    unsigned int spins = 0;
+                    int ab = 0;
+                    while (ld_acquire_gpu_u32(st.arrive + m) < n) {
+                        if ((++spins & 255u) == 0u) {
+                            if (*reinterpret_cast<volatile unsigned int*>(st.abort_w)) { ab = 1; break; }
+                            if (global_timer_ns() - t0 > peer.timeout_ns) {
+                                atomicOr(flags, RC_FLAG_PEER_TIMEOUT);
+                                atomicExch(st.abort_w, 1u);
+                                ab = 1;
+                                break;
+                            }
+                        }
+                    }
+                    st.arrive[m] = 0u;          // nobody touches the counter again before the update below is published
+                    __threadfence();
+                    s_ctl[2] = ab;
+                }
+                __syncthreads();
+                if (s_ctl[2]) return false;
+                return sk_reduce_update_m<W_T>(m, (unsigned int)(it + 1), ph, st, M, flags, peer, lp_smem);
+            };
             int64_t t = t_lo;
             while (t < t_hi) {
                 const int ml = (int)(t / ph.tpm), m = ph.m0 + ml;
@@ -1556,29 +1605,35 @@ sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int
                 else sk_list_segment(B, rBg, ph.tpm, st, m, tile0, tile1, lp_smem, rg, dst, bad);
                 lap(resel ? 1 : 2);
                 // arrive on m (the pass functions end with a block barrier after the partial is written: thread 0's
-                // fence + atomic publishes the whole block's writes); the last CTA does the reduction, the exchange
-                // and the update that opens the next pass on m
+                // fence + atomic publishes the whole block's writes).  The FIRST CTA to arrive owns the follow-up
+                // (reduce, exchange, update) -- the work lands on a CTA that has time to spare, not on the slowest one
+                // (which would then be late for its next segment, stay the slowest, and stretch every pass by the
+                // update) -- and it does so after the LAST segment of its range in this half, when the other CTAs of
+                // m have normally arrived too.
                 if (bad) {
                     atomicOr(flags, bad);
                     bad = 0;
                 }
                 if (threadIdx.x == 0) {
                     __threadfence();
-                    const unsigned int prev = atomicAdd(st.arrive + m, 1u);
-                    const int last = prev + 1u == (unsigned int)sk_ctas_of_m(ph, m);
-                    if (last) {
-                        st.arrive[m] = 0u;          // nobody touches the counter again before the update below is published
-                        __threadfence();
-                    }
-                    s_ctl[1] = last;
+                    s_ctl[1] = atomicAdd(st.arrive + m, 1u) == 0u ? 1 : 0;
                 }
                 __syncthreads();
                 if (s_ctl[1]) {
-                    if (!sk_reduce_update_m<W_T>(m, (unsigned int)(it + 1), ph, st, M, flags, peer, lp_smem)) return;
+                    if (n_own == 2) {          // (more than two sub-vectors in one range: settle the oldest now)
+                        if (!settle(own_m[0])) return;
+                        own_m[0] = own_m[1];
+                        n_own = 1;
+                    }
+                    own_m[n_own++] = m;
                 }
+                __syncthreads();               // s_ctl[1] is rewritten by the next arrival
                 lap(3);
                 t = t_end;
             }
+            for (int i = 0; i < n_own; ++i)
+                if (!settle(own_m[i])) return;
+            lap(3);
         }
     }
     if (threadIdx.x == 0) {
@@ -1706,6 +1761,27 @@ static int launch_update(const SkState& s, int M, int K, int sparse, unsigned in
                          M / 2, u, flags));
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
+}
+
+static int launch_reduce_update(const SkPart& pa, const SkPart& pb, const SkState& s, int M, int K, int sparse,
+                                unsigned int u, int32_t* flags, cudaStream_t st) {
+    RC_CUDA(launch_chain(sinkhorn_reduce_update_kernel, (unsigned)M, 256u, 0, st, pa, pb, s, K, (sparse && u > 0) ? 1 : 0,
+                         sparse, M / 2, u, flags));
+    RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
+    return RC_OK;
+}
+
+// RC_SINKHORN_PERSISTENT=1 / 0 forces the persistent kernel on / off for a single rank (default: off -- measured on
+// B200, one rank: two launches per iteration with programmatic dependent launch cost ~14 us of overhead per
+// iteration, the persistent kernel's arrivals, waits and in-kernel updates ~22 us; between ranks the persistent
+// kernel is the one that carries the fused exchange and is always used)
+static bool persistent_single_rank() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RC_SINKHORN_PERSISTENT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 static int loop_smem_attr() {
@@ -1968,16 +2044,15 @@ static int sinkhorn_solve_impl(float* table, const float* minmax, int64_t B, int
     }
     if (iters >= 1) {
         bool looped = false;
-        if (sparse) {
+        if (sparse && (peer.W > 1 || persistent_single_rank())) {
             rc = launch_loop(table, B, B_global, M, eps, iters - 1, p, p2, s, flags, peer, st);
             if (rc == RC_OK) looped = true;
             else if (rc != RC_E_UNSUPPORTED || peer.W > 1) return rc;
         }
         if (!looped) {
             for (int it = 0; it < iters; ++it) {
-                rc = (sparse && it > 0) ? launch_reduce(p2.h[0], p2.h[1], s, M, K, st) : launch_reduce(p, p, s, M, K, st);
-                if (rc) return rc;
-                rc = launch_update(s, M, K, sparse ? 1 : 0, (unsigned int)it, flags, st);
+                rc = (sparse && it > 0) ? launch_reduce_update(p2.h[0], p2.h[1], s, M, K, 1, (unsigned int)it, flags, st)
+                                        : launch_reduce_update(p, p, s, M, K, sparse ? 1 : 0, (unsigned int)it, flags, st);
                 if (rc) return rc;
                 if (it == iters - 1) break;
                 if (sparse) rc = launch_sparse_step(table, B, B_global, M, eps, p2, s, (unsigned int)it, flags, st);

@@ -31,4 +31,10 @@ for i, nm in enumerate(["wait", "selection", "list", "arrive+update"]):
 busy = t[:, 1] + t[:, 2]
 print(f"  busy (sel+list): min {busy.min():.1f} max {busy.max():.1f}; even/odd CTA mean {busy[0::2].mean():.1f} / {busy[1::2].mean():.1f}")
 print("  busy of CTAs 0..15:", np.round(busy[:16]).tolist())
+if os.environ.get("PROF_ALL"):
+    np.set_printoptions(linewidth=200)
+    print("  list us, all CTAs (rows of 37):")
+    print(np.round(t[:, 2]).astype(int).reshape(-1, 37))
+    print("  selection us:")
+    print(np.round(t[:, 1]).astype(int).reshape(-1, 37))
 print("codes checksum", int(codes.sum().item()))
