@@ -340,11 +340,15 @@ struct SkPart2 {
     SkPart h[2];
 };
 
+// The split pays only inside the persistent kernel; the launch chain (the default) gains nothing from it and pays
+// the per-segment overhead twice, so it runs with an empty first half (one contiguous range per CTA).
+static bool persistent_single_rank();
+
 static SkPart2 sk_partition2(int64_t B, int M, int ctas_per_sm) {
     SkPart2 q;
     const int64_t tpm = (B + SK_TILE - 1) / SK_TILE;
     const int G = num_sms() * ctas_per_sm;
-    const int Ma = M / 2, Mb = M - Ma;
+    const int Ma = persistent_single_rank() ? M / 2 : 0, Mb = M - Ma;
     const int Sa = Ma > 0 ? sk_part_slots(tpm * Ma, tpm, G) : 0, Sb = sk_part_slots(tpm * Mb, tpm, G);
     q.h[0] = SkPart{tpm, tpm * Ma, G, Sa, 0, 0, Sa + Sb};
     q.h[1] = SkPart{tpm, tpm * Mb, G, Sb, Ma, Sa, Sa + Sb};
@@ -370,6 +374,7 @@ struct SkState {
     unsigned char* pool; // survivor records (layout below)
     double* U;           // (M,K)  2^(lu - lu_build - max_k(lu - lu_build)): per-column factor since selection
     unsigned long long* cta_ns;  // (G,4) diagnostics: ns per CTA in wait / selection / list / arrive+update
+    int m_half1;         // first sub-vector of the second half of the iteration partition (SkPart2)
     uint32_t row_cap;    // test hook: a row with more survivors than this raises RC_FLAG_SPARSE_UNSAFE (256 = never)
     double slack;        // selection depth beyond SK_MARGIN (log2 units)
 };
@@ -460,6 +465,7 @@ static size_t sk_layout(int64_t B, int M, int K, const SkPart& p, void* base, Sk
         s->cta_ns = (unsigned long long*)(b + o_dbg);
         s->pool = (unsigned char*)(b + o_pool);
         s->slack = sk_slack();
+        s->m_half1 = sk_partition2(B, M, 2).h[1].m0;
         s->row_cap = (g_pool_entries_override > 0 && g_pool_entries_override < 256) ? (uint32_t)g_pool_entries_override : 256u;
         s->lu = (double*)(b + o_lu);
         s->P = (double*)(b + o_P);
@@ -1433,11 +1439,8 @@ __host__ __device__ constexpr size_t sk_peer_header_bytes(int M) { return (size_
 // reduce + (exchange) + update of sub-vector m by one block; u = index of the update (0 = after BEGIN)
 template <int W_T>
 __device__ __forceinline__ bool sk_reduce_update_m(int m, unsigned int u, const SkPart& part, const SkState& st, int M,
-                                                   int32_t* __restrict__ flags, const SkPeer& peer,
-                                                   unsigned char* smem) {
-    int* s_off = reinterpret_cast<int*>(smem + LOOP_OFF_RED);          // the reduction scratch is free here
-    double* s_red = reinterpret_cast<double*>(smem + LOOP_OFF_MISC);
-    int* s_flag = reinterpret_cast<int*>(smem + LOOP_OFF_MISC + 18 * 8);
+                                                   int32_t* __restrict__ flags, const SkPeer& peer, int* s_off,
+                                                   double* s_red, int* s_flag) {
     sk_reduce_m(m, st.partial, part, SP_K, st.P, s_off);
     if (W_T != 1) {
         const int W = W_T > 0 ? W_T : peer.W;
@@ -1486,8 +1489,25 @@ __device__ __forceinline__ bool sk_reduce_update_m(int m, unsigned int u, const 
         __stcg(st.P + (int64_t)m * SP_K + threadIdx.x, sum);
     }
     __syncthreads();
-    sk_update_m(m, st, SP_K, u > 0 ? 1 : 0, 1, m >= M / 2 ? 1 : 0, u, flags, s_red);
+    sk_update_m(m, st, SP_K, u > 0 ? 1 : 0, 1, m >= st.m_half1 ? 1 : 0, u, flags, s_red);
     return true;
+}
+
+// The exchange fused into the row-sum kernel of the launch chain (W ranks): block m reduces the partials of m,
+// publishes the 256 sums to the peers, waits for theirs, sums in rank order from peer memory and updates the row
+// scaling -- the three kernels reduce / all-reduce / update of the step-wise sequence in one launch, the
+// reference's `dist.all_reduce(sum_of_rows)` (modeling_repconc.py:156-157) without a collective call.
+template <int W_T>
+__global__ void __launch_bounds__(256)
+sinkhorn_reduce_exchange_update_kernel(SkPart pa, SkPart pb, SkState st, int M, unsigned int u,
+                                       int32_t* __restrict__ flags, SkPeer peer) {
+    __shared__ int s_off[SK_RED_LIST];
+    __shared__ double s_red[18];
+    __shared__ int s_flag;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int m = blockIdx.x;
+    sk_reduce_update_m<W_T>(m, u, m < pb.m0 ? pa : pb, st, M, flags, peer, s_off, s_red, &s_flag);
 }
 
 template <int W_T>
@@ -1496,12 +1516,15 @@ sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int
                      SkPart2 part, SkState st, int n_pass, int32_t* __restrict__ flags, SkPeer peer) {
     extern __shared__ __align__(128) unsigned char lp_smem[];
     int* s_ctl = reinterpret_cast<int*>(lp_smem + LOOP_OFF_MISC + 18 * 8 + 8);   // {decision word, last, abort}
+    int* l_off = reinterpret_cast<int*>(lp_smem + LOOP_OFF_RED);          // (the reduction scratch is free between passes)
+    double* l_red = reinterpret_cast<double*>(lp_smem + LOOP_OFF_MISC);
+    int* l_flag = reinterpret_cast<int*>(lp_smem + LOOP_OFF_MISC + 18 * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     // the row scaling after BEGIN (update 0; BEGIN's partials follow its own single-range partition), dealt out
     // over the CTAs
     for (int m = g; m < M; m += gridDim.x)
-        if (!sk_reduce_update_m<W_T>(m, 0u, part_begin, st, M, flags, peer, lp_smem)) return;
+        if (!sk_reduce_update_m<W_T>(m, 0u, part_begin, st, M, flags, peer, l_off, l_red, l_flag)) return;
     if (n_pass <= 0) return;
     SkRings rg = {0u, 0u, 0u, 0u};
     if (lane == 0) {
@@ -1591,7 +1614,7 @@ sinkhorn_loop_kernel(const float* __restrict__ table, int64_t B, double rBg, int
                 }
                 __syncthreads();
                 if (s_ctl[2]) return false;
-                return sk_reduce_update_m<W_T>(m, (unsigned int)(it + 1), ph, st, M, flags, peer, lp_smem);
+                return sk_reduce_update_m<W_T>(m, (unsigned int)(it + 1), ph, st, M, flags, peer, l_off, l_red, l_flag);
             };
             int64_t t = t_lo;
             while (t < t_hi) {
@@ -1758,7 +1781,7 @@ static int launch_reduce(const SkPart& pa, const SkPart& pb, const SkState& s, i
 // sparse pass always selects)
 static int launch_update(const SkState& s, int M, int K, int sparse, unsigned int u, int32_t* flags, cudaStream_t st) {
     RC_CUDA(launch_chain(sinkhorn_update_kernel, (unsigned)M, 256u, 0, st, s, K, (sparse && u > 0) ? 1 : 0, sparse,
-                         M / 2, u, flags));
+                         s.m_half1, u, flags));
     RC_CHECK_LAUNCH("sinkhorn_update_kernel");
     return RC_OK;
 }
@@ -1766,15 +1789,29 @@ static int launch_update(const SkState& s, int M, int K, int sparse, unsigned in
 static int launch_reduce_update(const SkPart& pa, const SkPart& pb, const SkState& s, int M, int K, int sparse,
                                 unsigned int u, int32_t* flags, cudaStream_t st) {
     RC_CUDA(launch_chain(sinkhorn_reduce_update_kernel, (unsigned)M, 256u, 0, st, pa, pb, s, K, (sparse && u > 0) ? 1 : 0,
-                         sparse, M / 2, u, flags));
+                         sparse, s.m_half1, u, flags));
     RC_CHECK_LAUNCH("sinkhorn_reduce_update_kernel");
     return RC_OK;
 }
 
+static int launch_reduce_exchange_update(const SkPart& pa, const SkPart& pb, const SkState& s, int M, unsigned int u,
+                                         int32_t* flags, const SkPeer& peer, cudaStream_t st) {
+    void (*kern)(SkPart, SkPart, SkState, int, unsigned int, int32_t*, SkPeer);
+    switch (peer.W) {
+        case 2: kern = sinkhorn_reduce_exchange_update_kernel<2>; break;
+        case 4: kern = sinkhorn_reduce_exchange_update_kernel<4>; break;
+        case 8: kern = sinkhorn_reduce_exchange_update_kernel<8>; break;
+        default: kern = sinkhorn_reduce_exchange_update_kernel<0>; break;
+    }
+    RC_CUDA(launch_chain(kern, (unsigned)M, 256u, 0, st, pa, pb, s, M, u, flags, peer));
+    RC_CHECK_LAUNCH("sinkhorn_reduce_exchange_update_kernel");
+    return RC_OK;
+}
+
 // RC_SINKHORN_PERSISTENT=1 / 0 forces the persistent kernel on / off for a single rank (default: off -- measured on
-// B200, one rank: two launches per iteration with programmatic dependent launch cost ~14 us of overhead per
-// iteration, the persistent kernel's arrivals, waits and in-kernel updates ~22 us; between ranks the persistent
-// kernel is the one that carries the fused exchange and is always used)
+// B200: two launches per iteration with programmatic dependent launch cost ~14 us of overhead per iteration, the
+// persistent kernel's arrivals, waits and in-kernel updates ~22 us -- at one rank and at two.  Between ranks both
+// carry the exchange inside a kernel: the chain in its row-sum kernel, the persistent kernel in its update step)
 static bool persistent_single_rank() {
     static int v = -1;
     if (v < 0) {
@@ -2044,15 +2081,20 @@ static int sinkhorn_solve_impl(float* table, const float* minmax, int64_t B, int
     }
     if (iters >= 1) {
         bool looped = false;
-        if (sparse && (peer.W > 1 || persistent_single_rank())) {
+        if (sparse && persistent_single_rank()) {
             rc = launch_loop(table, B, B_global, M, eps, iters - 1, p, p2, s, flags, peer, st);
             if (rc == RC_OK) looped = true;
-            else if (rc != RC_E_UNSUPPORTED || peer.W > 1) return rc;
+            else if (rc != RC_E_UNSUPPORTED) return rc;
         }
         if (!looped) {
             for (int it = 0; it < iters; ++it) {
-                rc = (sparse && it > 0) ? launch_reduce_update(p2.h[0], p2.h[1], s, M, K, 1, (unsigned int)it, flags, st)
-                                        : launch_reduce_update(p, p, s, M, K, sparse ? 1 : 0, (unsigned int)it, flags, st);
+                const bool two = sparse && it > 0;       // which partition wrote the partials
+                if (peer.W > 1)
+                    rc = launch_reduce_exchange_update(two ? p2.h[0] : p, two ? p2.h[1] : p, s, M, (unsigned int)it, flags,
+                                                       peer, st);
+                else
+                    rc = launch_reduce_update(two ? p2.h[0] : p, two ? p2.h[1] : p, s, M, K, sparse ? 1 : 0,
+                                              (unsigned int)it, flags, st);
                 if (rc) return rc;
                 if (it == iters - 1) break;
                 if (sparse) rc = launch_sparse_step(table, B, B_global, M, eps, p2, s, (unsigned int)it, flags, st);

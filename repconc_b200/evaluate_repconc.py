@@ -81,6 +81,8 @@ def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarr
             and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
         # position -> corpus id on the device, before the copy back (same values as :183)
         topk_scores, topk_ids = index.search(query_embeds, topk, corpus_ids=corpus_ids)
+        if isinstance(index, ShardedSearcher) and index.rank != 0:
+            return topk_scores, topk_ids                     # empty on the ranks that do not receive the result
     else:
         topk_scores, topk_idx = index.search(query_embeds, topk)
         topk_ids = corpus_ids[topk_idx]      # == np.vstack([corpus_ids[x] for x in topk_idx]) (:183)
@@ -98,7 +100,8 @@ def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np
         # same batches (np.array_split, :193-197), searched back to back with the copy-back of one batch
         # overlapping the scan of the next
         scores, ids = index.search_batches(np.array_split(query_embeds, iterations), topk, corpus_ids=corpus_ids)
-        assert len(query_ids) == len(scores) == len(ids)
+        # (a multi-process ShardedSearcher delivers the merged result on rank 0 only; the other ranks get empty arrays)
+        assert len(scores) == len(ids) and len(scores) in (len(query_ids), 0)
         return scores, ids
     for query_id_iter, query_embeds_iter in tqdm(zip(
         np.array_split(query_ids, iterations),

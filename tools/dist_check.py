@@ -42,21 +42,46 @@ def main():
         g = np.load(os.path.join(ROOT, "tests", "golden", "assign_dist2_ds16.npz"))
         a_ok = a_ok and bool(np.array_equal(got, g["codes_conc"].astype(np.int64)))
     ok &= a_ok
-    # --- larger assign (BASELINE config 5 shape per rank, fewer iterations), vs single-process global batch
-    gen = torch.Generator(device=dev).manual_seed(3)
-    cg = torch.randn((96, 256, 8), generator=gen, device=dev)
-    xg = torch.randn((world * 1024, 768), generator=gen, device=dev)                 # same on every rank
-    cd = ops.constrained_assign(xg[rank * 1024:(rank + 1) * 1024], cg, 0.003, 12)
-    cs = ops.constrained_assign(xg, cg, 0.003, 12, distributed=False)[rank * 1024:(rank + 1) * 1024]
-    b_ok = bool(torch.equal(cd, cs))
+    # --- BASELINE-size assignments (global batch 8192, M = 48 and M = 96, T = 50) sharded over the ranks, against
+    #     the codes the REFERENCE produced for the global batch (goldens assign_m48_b8192 / assign_m96_b8192;
+    #     the reference's distributed run is the same computation: sums over the global batch, B *= world)
+    b_ok = True
+    for name in ("m48_b8192", "m96_b8192"):
+        bc = GC.ASSIGN_BIG_CASES[name]
+        gb = np.load(os.path.join(ROOT, "tests", "golden", f"assign_{name}.npz"))
+        xb, cb = GC.assign_inputs(bc)
+        perb = bc["B"] // world
+        cd = ops.constrained_assign(torch.from_numpy(xb[rank * perb:(rank + 1) * perb]).to(dev),
+                                    torch.from_numpy(cb).to(dev), bc["eps"], bc["iters"])
+        wantb = gb["codes_conc"][rank * perb:(rank + 1) * perb].astype(np.int64)
+        nbad = int((cd.cpu().numpy() != wantb).sum())
+        if nbad:
+            print(f"rank {rank}: {name}: {nbad} code mismatches vs the reference", flush=True)
+        b_ok = b_ok and nbad == 0
     ok &= b_ok
+    # --- RC_FLAG_SPARSE_UNSAFE raised on ONE rank only (rank 1 pretends its survivor records hold 8 entries): the
+    #     flag word is OR-ed over the ranks, every rank re-runs densely in lock step, codes stay the reference's
+    from repconc_b200 import _lib
+    lib = _lib.load()
+    prev = lib.rc_sinkhorn_debug_pool_entries(8 if rank == 1 else 0)
+    try:
+        codes2 = ops.constrained_assign(xs, torch.from_numpy(c).to(dev), case["eps"], case["iters"])
+    finally:
+        lib.rc_sinkhorn_debug_pool_entries(prev)
+    allc2 = [torch.empty_like(codes2.contiguous()) for _ in range(world)]
+    dist.all_gather(allc2, codes2.contiguous())
+    u_ok = bool(np.array_equal(torch.cat(allc2, 0).cpu().numpy(), want))
+    ok &= u_ok
     # --- sharded ADC
     q, cc, codes_h = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
     lo, hi = E.shard_bounds(len(codes_h), rank, world)
     shard = GpuIndexPQ(torch.from_numpy(codes_h[lo:hi]).to(dev), torch.from_numpy(cc).to(dev), id_offset=lo)
-    s, i = E.sharded_search(shard, q, 100)
+    s, i = E.sharded_search(shard, torch.from_numpy(q).to(dev), 100)      # CUDA tensors in -> result on every rank
+    # host arrays in (the evaluator's batch_search): rank 0 receives the merged result, the others empty arrays
+    hs, hi_ = E.batch_search(np.arange(len(q)), q, np.arange(len(codes_h), dtype=np.int64), E.ShardedSearcher(shard), 100, 24)
     so, io = O.adc_search(q, cc, codes_h, 100)
     s_ok = bool(np.array_equal(s.cpu().numpy(), so) and np.array_equal(i.cpu().numpy(), io))
+    s_ok = s_ok and (bool(np.array_equal(hs, so) and np.array_equal(hi_, io)) if rank == 0 else len(hs) == 0)
     ok &= s_ok
     # --- peer-memory all-reduce (rc_peer_allreduce_f64) vs a rank-ordered sum of all-gathered vectors
     from repconc_b200.peer import PeerAllReduce
@@ -80,7 +105,8 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"dist_check world={world}: assign_golden={a_ok} assign_global_batch={b_ok} sharded_adc={s_ok} "
+        print(f"dist_check world={world}: assign_golden={a_ok} assign_baseline_size_vs_reference={b_ok} "
+              f"one_rank_unsafe_flag_dense_rerun={u_ok} sharded_adc={s_ok} "
               f"peer_allreduce={'exact' if (p_used and p_ok) else ('MISMATCH' if p_used else 'unavailable (NCCL used)')} "
               f"-> {'PASS' if flag.item() == 1 else 'FAIL'}")
     dist.destroy_process_group()
