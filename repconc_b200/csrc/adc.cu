@@ -275,6 +275,9 @@ struct PackScanArgs {
     int64_t blk, stride;
     uint16_t* out16;
     int64_t ld16;
+    // conflict-free kernel: work items = (split, tile), handed out through item_ctr
+    int64_t tiles, splits;
+    unsigned int* item_ctr;
 };
 
 template <int QP, int MT>
@@ -347,121 +350,316 @@ adc_scan_packed_kernel(PackScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// bank-conflict-free variant of the packed scan (M % 8 == 0, 8 queries per entry).
-// The thread-per-document kernel above gathers at random 16-byte bank groups: ncu shows 2.5 wavefronts
-// per ideal wavefront and the LSU wavefront pipe at 98.8 % -- it IS the shared-memory crossbar limit.
-// Here the table is laid out [k][m] (m fastest) and the 8 lanes of a quarter-warp take 8 CONSECUTIVE
-// sub-vectors of ONE document: entry index = code*M + m, so the bank group (index mod 8) equals the lane
-// index inside the quarter whatever the codes are -- every LDS.128 phase is conflict-free.  A warp works
-// on 4 documents at a time; each lane accumulates M/8 entries, then the 8 partial 4-word accumulators
-// of a document are reduced with a halving exchange (4 shuffles instead of 12) that leaves lane j of the
-// quarter with the complete 16-bit sums of query j -- which it compares with that query's threshold.
+// fused LUT + quantise + pack: one CTA per tile of QP queries.  Thread k holds centroid k; for every
+// sub-vector it forms the QP inner products (fp32, j ascending, multiply then add: the oracle's order),
+// writes the fp32 table (the exact re-score reads it), tracks min / max per (query, sub-vector); a second
+// sweep quantises (the arithmetic of adc_quantise_lut_kernel, value for value) and writes the tile's
+// integer tables in exactly the layout the conflict-free scan keeps in shared memory, [k][m][QP] uint16,
+// so that the scan stages a tile with a few bulk copies instead of 2-byte transposing stores.
+// Replaces adc_lut_kernel (0.44 ms per 1200 queries: one CTA per (query, sub-vector), every centroid re-read
+// per query) + adc_quantise_lut_kernel (0.09 ms).
 // ---------------------------------------------------------------------------------------------
-constexpr int CF_THREADS = 1024;   // 32 warps: the gathers are latency-bound at 16
-
-template <int MT, bool SAMPLE>
-__global__ void __launch_bounds__(CF_THREADS, 1)
-adc_scan_cf_kernel(PackScanArgs a) {
-    static_assert(MT % 8 == 0, "8 consecutive sub-vectors per quarter-warp");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint4* lutS = reinterpret_cast<const uint4*>(smem_raw);  // [256][MT], 8 x uint16 per entry
-    const int64_t q0 = (int64_t)blockIdx.x * 8;
-    const int nqt = (int)min((int64_t)8, a.nq - q0);
-    {
-        uint16_t* lh = reinterpret_cast<uint16_t*>(smem_raw);
-        const int n = MT * ADC_K;
-        for (int qq = 0; qq < 8; ++qq) {
-            const uint16_t* src = a.qlut + (q0 + qq) * (int64_t)n;
-            for (int i = threadIdx.x; i < n; i += CF_THREADS) {
-                const int m = i >> 8, k = i & 255;
-                lh[(k * MT + m) * 8 + qq] = qq < nqt ? src[i] : (uint16_t)0;
-            }
-        }
+template <int QP>
+__global__ void __launch_bounds__(256)
+adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float* __restrict__ c, int64_t nq, int M,
+                    int ds, int qmax, float* __restrict__ lut, uint16_t* __restrict__ qpack,
+                    float* __restrict__ step_out, double* __restrict__ sumlo_out, double* __restrict__ sumabs_out) {
+    extern __shared__ __align__(16) float lp_sh[];
+    const int D = M * ds;
+    float* qs = lp_sh;                         // [QP][D]
+    float* q_lo = qs + QP * D;                 // [QP][M]
+    float* red = q_lo + QP * M;                // [8 warps][QP][2]
+    float* s_step = red + 8 * QP * 2;          // [QP]
+    const int64_t tile = blockIdx.x;
+    const int64_t q0 = tile * QP;
+    const int nqt = (int)min((int64_t)QP, nq - q0);
+    const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+    for (int i = k; i < QP * D; i += 256) {
+        const int qq = i / D, d = i - qq * D;
+        qs[i] = qq < nqt ? queries[(q0 + qq) * ldq + d] : 0.0f;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = lane & 7, sub = lane >> 3;
-    const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0;
-    const int my_thr = (!SAMPLE && j < nqt) ? a.thr_i[q0 + j] : 0x7fffffff;   // lane j of a quarter owns query j
     __syncthreads();
-
-    const int64_t p_lo = (int64_t)blockIdx.y * a.pos_per_split;
-    const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
-    constexpr int DOCS_PER_IT = (CF_THREADS / 32) * 4;   // 128 documents per CTA iteration, 4 per warp
-
-    // one group of 4 documents: gather, halving exchange over the quarter-warp (after it lane j holds the
-    // 16-bit sum of query j), threshold test
-    auto scan_group = [&](const uint32_t (&cb)[MT / 8], int64_t p, bool live) {
-        uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    float range = 0.0f;                        // thread qq < QP tracks its query
+    double sumabs = 0.0, sumlo = 0.0;
+    for (int m = 0; m < M; ++m) {
+        const float* ck = c + ((int64_t)m * ADC_K + k) * ds;
+        float sacc[QP];
 #pragma unroll
-        for (int i = 0; i < MT / 8; ++i) {
-            const uint4 v = lutS[cb[i] * MT + 8 * i + j];
-            acc0 += v.x; acc1 += v.y; acc2 += v.z; acc3 += v.w;
-        }
-        const uint32_t s0 = b2 ? acc0 : acc2, s1 = b2 ? acc1 : acc3;
-        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
-        const uint32_t k0 = (b2 ? acc2 : acc0) + r0, k1 = (b2 ? acc3 : acc1) + r1;
-        const uint32_t s2 = b1 ? k0 : k1;
-        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 2);
-        uint32_t w = (b1 ? k1 : k0) + r2;
-        w += __shfl_xor_sync(0xffffffffu, w, 1);
-        const int sum = (int)((w >> (16 * (j & 1))) & 0xffffu);
-        if (SAMPLE) {
-            if (live && j < nqt) a.out16[(q0 + j) * a.ld16 + p] = (uint16_t)sum;
-        } else if (live && sum >= my_thr) {
-            const unsigned int pos = atomicAdd(a.cnt + q0 + j, 1u);
-            if (pos < (unsigned int)a.cap) a.cand[(q0 + j) * (int64_t)a.cap + pos] = (uint32_t)p;
-        }
-    };
-    // position -> first code byte of this lane (sample mode scans evenly spaced blocks of the corpus)
-    auto code_ptr = [&](int64_t pos) {
-        const int64_t doc = SAMPLE ? (pos / a.blk) * a.stride + (pos % a.blk) : pos;
-        return a.codes + doc * MT + j;
-    };
-
-    // full iterations (every document of every warp's group is inside the split): no predicates, code bytes
-    // of the next group are loaded while this one is scanned
-    const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
-    int64_t p = p_lo + warp * 4 + sub;
-    const uint8_t* cp = code_ptr(p);
-    uint32_t cb[MT / 8], cn[MT / 8];
-    if (full > 0) {
+        for (int qq = 0; qq < QP; ++qq) sacc[qq] = 0.0f;
+        for (int j = 0; j < ds; ++j) {
+            const float cj = __ldg(ck + j);
 #pragma unroll
-        for (int i = 0; i < MT / 8; ++i) cb[i] = __ldg(cp + 8 * i);
+            for (int qq = 0; qq < QP; ++qq) sacc[qq] = __fadd_rn(sacc[qq], __fmul_rn(qs[qq * D + m * ds + j], cj));
+        }
+#pragma unroll
+        for (int qq = 0; qq < QP; ++qq) {
+            if (qq < nqt) lut[((q0 + qq) * M + m) * ADC_K + k] = sacc[qq];
+            const float lo = warp_min(sacc[qq]), hi = warp_max(sacc[qq]);
+            if (lane == 0) { red[(warp * QP + qq) * 2] = lo; red[(warp * QP + qq) * 2 + 1] = hi; }
+        }
+        __syncthreads();
+        if (k < QP) {
+            float l = red[k * 2], h = red[k * 2 + 1];
+            for (int w = 1; w < 8; ++w) { l = fminf(l, red[(w * QP + k) * 2]); h = fmaxf(h, red[(w * QP + k) * 2 + 1]); }
+            q_lo[k * M + m] = l;
+            range = fmaxf(range, h - l);
+            sumabs += (double)fmaxf(fabsf(l), fabsf(h));
+            sumlo += (double)l;
+        }
+        __syncthreads();
     }
-    for (int64_t t = 0; t < full; ++t) {
-        if (t + 1 < full) {
-            const uint8_t* cq = SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT;
-#pragma unroll
-            for (int i = 0; i < MT / 8; ++i) cn[i] = __ldg(cq + 8 * i);
+    if (k < QP) {
+        // a degenerate (constant) table still needs a positive step
+        const float step = fmaxf(range, 1e-30f) / (float)qmax;
+        s_step[k] = step;
+        if (k < nqt) {
+            step_out[q0 + k] = step;
+            sumlo_out[q0 + k] = sumlo;
+            sumabs_out[q0 + k] = sumabs;
         }
-        scan_group(cb, p, true);
-#pragma unroll
-        for (int i = 0; i < MT / 8; ++i) cb[i] = cn[i];
-        p += DOCS_PER_IT;
-        cp += (int64_t)DOCS_PER_IT * MT;
     }
-    // tail: fewer than DOCS_PER_IT documents left in the split
-    if (p_lo + full * DOCS_PER_IT < p_hi) {   // block-uniform
-        const bool live = p < p_hi;
-        const uint8_t* ct = live ? code_ptr(p) : a.codes + j;
+    __syncthreads();
+    // second sweep: quantise this thread's own column k of every (query, sub-vector) and write the entries
+    uint16_t* tp = qpack + (size_t)tile * M * ADC_K * QP;
+    for (int m = 0; m < M; ++m) {
+        uint32_t w[QP / 2];
 #pragma unroll
-        for (int i = 0; i < MT / 8; ++i) cb[i] = live ? (uint32_t)__ldg(ct + 8 * i) : 0u;
-        scan_group(cb, p, live);
+        for (int i = 0; i < QP / 2; ++i) w[i] = 0u;
+#pragma unroll
+        for (int qq = 0; qq < QP; ++qq) {
+            int qi = 0;
+            if (qq < nqt) {
+                const float v = lut[((q0 + qq) * M + m) * ADC_K + k];
+                qi = __float2int_rn((v - q_lo[qq * M + m]) / s_step[qq]);
+                qi = qi < 0 ? 0 : (qi > qmax ? qmax : qi);
+            }
+            w[qq >> 1] |= (uint32_t)qi << (16 * (qq & 1));
+        }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tp + ((size_t)k * M + m) * QP);
+        if constexpr (QP == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
     }
 }
 
-template <int MT, bool SAMPLE = false>
-static int launch_cf_inst(const PackScanArgs& a, int splits, cudaStream_t st) {
-    auto kern = adc_scan_cf_kernel<MT, SAMPLE>;
-    const size_t smem = (size_t)MT * ADC_K * 16;
+// ---------------------------------------------------------------------------------------------
+// bank-conflict-free packed scan.  The thread-per-document kernel above gathers at random 16-byte bank
+// groups: ncu shows 2.5 wavefronts per ideal wavefront and the LSU wavefront pipe at 98.8 % -- it IS the
+// shared-memory crossbar limit.  Here the table is laid out [k][m] (m fastest) and the lanes that share a
+// document take CONSECUTIVE sub-vectors of it: entry index = code*M + m, so the bank group of an access equals
+// the lane's position among the lanes of its document whatever the codes are -- every shared-memory phase is
+// conflict-free.
+//   QP = 8 (M % 8 == 0, M <= 48): 16-byte entries (8 queries x uint16), 8 lanes per document (a quarter-warp),
+//       4 documents per warp at a time; each lane accumulates M/8 entries, then the 8 partial 4-word
+//       accumulators of a document are reduced with a halving exchange (4 shuffles instead of 12) that leaves
+//       lane j of the quarter with the complete 16-bit sums of query j.
+//   QP = 4 (M % 16 == 0, M <= 96 -- the reference's M = 64 and BASELINE's M = 96): 8-byte entries (4 queries),
+//       16 lanes per document (a half-warp: an LDS.64 phase covers 16 lanes), 2 documents per warp at a time;
+//       one halving exchange and a 3-step butterfly leave every lane of an 8-lane group with the sums of two
+//       queries.  The tables of wide codes do not fit at 8 queries (M * 256 * 16 B = 256 KB at M = 64).
+// Work distribution: CTAs are persistent (one per SM -- the tables fill the shared memory) and take ITEMS
+// = (split of the corpus, tile of QP queries) from an atomic counter, tile fastest: at any moment the CTAs work on
+// the same few-MB split of the codes (L2-resident) for different query tiles, the load is balanced to one item
+// (~32k documents) whatever the shard size, and a tile's tables (already in the shared-memory layout, see
+// adc_lut_pack_kernel) arrive with bulk copies (TMA), ~2 us per item.
+// ---------------------------------------------------------------------------------------------
+constexpr int CF_THREADS = 1024;   // 32 warps: the gathers are latency-bound at 16
+
+template <int MT, int QP, bool SAMPLE>
+__global__ void __launch_bounds__(CF_THREADS, 1)
+adc_scan_cf_kernel(PackScanArgs a) {
+    static_assert(QP == 8 || QP == 4, "8 or 4 queries per entry");
+    constexpr int LPD = QP == 8 ? 8 : 16;                 // lanes per document
+    static_assert(MT % LPD == 0, "consecutive sub-vectors per lane group");
+    constexpr int NE = MT / LPD;                          // entries per lane
+    constexpr int DPW = 32 / LPD;                         // documents per warp at a time
+    constexpr int DOCS_PER_IT = (CF_THREADS / 32) * DPW;  // documents per CTA iteration
+    constexpr uint32_t TILE_BYTES = (uint32_t)MT * ADC_K * QP * 2;
+    using Entry = typename PackVec<QP>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Entry* lutS = reinterpret_cast<const Entry*>(smem_raw);  // [256][MT] entries
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_BYTES);
+    int* s_item = reinterpret_cast<int*>(smem_raw + TILE_BYTES + 8);
+    const uint32_t bar_a = smem_u32(bar);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & (LPD - 1), sub = lane / LPD;
+    if (threadIdx.x == 0) mbar_init(bar_a, 1);
+    fence_barrier_init();
+    __syncthreads();
+    const int64_t total = a.tiles * a.splits;
+    int64_t cur_tile = -1;
+    uint32_t phase = 0;
+    int my_thr = 0x7fffffff;
+    int64_t q0 = 0;
+    int nqt = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) *s_item = (int)atomicAdd(a.item_ctr, 1u);
+        __syncthreads();                                  // (also: every gather of the previous item has been consumed)
+        const int64_t item = *s_item;
+        __syncthreads();                                  // s_item is rewritten by the next fetch
+        if (item >= total) break;
+        const int64_t tile = item % a.tiles, split = item / a.tiles;
+        if (tile != cur_tile) {
+            if (threadIdx.x == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar_a, TILE_BYTES);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)tile * TILE_BYTES;
+                for (uint32_t o = 0; o < TILE_BYTES; o += 32768u)
+                    bulk_load(smem_raw + o, src + o, min(32768u, TILE_BYTES - o), bar_a);
+            }
+            q0 = tile * QP;
+            nqt = (int)min((int64_t)QP, a.nq - q0);
+            // the lane that ends up with query qi's sum: QP = 8: lane j <-> query j; QP = 4: lanes (j & 7) < 2 of
+            // each 8-lane group <-> query 2 * (j >> 3) + (j & 1)
+            const int qi = QP == 8 ? j : ((j & 7) < 2 ? 2 * (j >> 3) + (j & 1) : QP);
+            my_thr = (!SAMPLE && qi < nqt) ? a.thr_i[q0 + qi] : 0x7fffffff;
+            mbar_wait(bar_a, phase);
+            phase ^= 1u;
+            cur_tile = tile;
+        }
+        const int qi = QP == 8 ? j : ((j & 7) < 2 ? 2 * (j >> 3) + (j & 1) : QP);
+        const int64_t p_lo = split * a.pos_per_split;
+        const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
+
+        // one group of DPW documents: gather, exchange over the document's lanes, threshold test
+        auto scan_group = [&](const uint32_t (&cb)[NE], int64_t p, bool live) {
+            int sum;
+            if constexpr (QP == 8) {
+                const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0;
+                uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const uint4 v = lutS[cb[i] * MT + 8 * i + j];
+                    acc0 += v.x; acc1 += v.y; acc2 += v.z; acc3 += v.w;
+                }
+                const uint32_t s0 = b2 ? acc0 : acc2, s1 = b2 ? acc1 : acc3;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+                const uint32_t k0 = (b2 ? acc2 : acc0) + r0, k1 = (b2 ? acc3 : acc1) + r1;
+                const uint32_t s2 = b1 ? k0 : k1;
+                const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 2);
+                uint32_t w = (b1 ? k1 : k0) + r2;
+                w += __shfl_xor_sync(0xffffffffu, w, 1);
+                sum = (int)((w >> (16 * (j & 1))) & 0xffffu);
+            } else {
+                const bool b3 = (j & 8) != 0;
+                uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const uint2 v = lutS[cb[i] * MT + 16 * i + j];
+                    acc0 += v.x; acc1 += v.y;
+                }
+                const uint32_t r = __shfl_xor_sync(0xffffffffu, b3 ? acc0 : acc1, 8);
+                uint32_t w = (b3 ? acc1 : acc0) + r;       // lanes 0-7: queries 0,1; lanes 8-15: queries 2,3
+                w += __shfl_xor_sync(0xffffffffu, w, 4);
+                w += __shfl_xor_sync(0xffffffffu, w, 2);
+                w += __shfl_xor_sync(0xffffffffu, w, 1);
+                sum = (int)((w >> (16 * (j & 1))) & 0xffffu);
+            }
+            if (SAMPLE) {
+                if (live && qi < nqt) a.out16[(q0 + qi) * a.ld16 + p] = (uint16_t)sum;
+            } else if (live && sum >= my_thr) {
+                const unsigned int pos = atomicAdd(a.cnt + q0 + qi, 1u);
+                if (pos < (unsigned int)a.cap) a.cand[(q0 + qi) * (int64_t)a.cap + pos] = (uint32_t)p;
+            }
+        };
+        // position -> first code byte of this lane (sample mode scans evenly spaced blocks of the corpus)
+        auto code_ptr = [&](int64_t pos) {
+            const int64_t doc = SAMPLE ? (pos / a.blk) * a.stride + (pos % a.blk) : pos;
+            return a.codes + doc * MT + j;
+        };
+        // full iterations (every document of every warp's group is inside the split): no predicates, code bytes
+        // of the next group are loaded while this one is scanned
+        const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
+        int64_t p = p_lo + warp * DPW + sub;
+        const uint8_t* cp = code_ptr(p);
+        uint32_t cb[NE], cn[NE];
+        if (full > 0) {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) cb[i] = __ldg(cp + LPD * i);
+        }
+        for (int64_t t = 0; t < full; ++t) {
+            if (t + 1 < full) {
+                const uint8_t* cq = SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT;
+#pragma unroll
+                for (int i = 0; i < NE; ++i) cn[i] = __ldg(cq + LPD * i);
+            }
+            scan_group(cb, p, true);
+#pragma unroll
+            for (int i = 0; i < NE; ++i) cb[i] = cn[i];
+            p += DOCS_PER_IT;
+            cp += (int64_t)DOCS_PER_IT * MT;
+        }
+        // tail: fewer than DOCS_PER_IT documents left in the split
+        if (p_lo + full * DOCS_PER_IT < p_hi) {   // block-uniform
+            const bool live = p < p_hi;
+            const uint8_t* ct = live ? code_ptr(p) : a.codes + j;
+#pragma unroll
+            for (int i = 0; i < NE; ++i) cb[i] = live ? (uint32_t)__ldg(ct + LPD * i) : 0u;
+            scan_group(cb, p, live);
+        }
+    }
+}
+
+// which conflict-free variant serves this M: 8 queries per entry, 4, or none (0)
+static int cf_qp(int M) {
+    if (M % 8 == 0 && M >= 8 && M <= 48) return 8;
+    if (M % 16 == 0 && M <= 96) return 4;
+    return 0;
+}
+static bool cf_capable(int M) { return cf_qp(M) != 0; }
+
+template <int MT, int QP, bool SAMPLE>
+static int launch_cf_inst(const PackScanArgs& a, cudaStream_t st) {
+    auto kern = adc_scan_cf_kernel<MT, QP, SAMPLE>;
+    const size_t smem = (size_t)MT * ADC_K * QP * 2 + 16;
     static unsigned long long attr_seen = 0ull;
     if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    dim3 grid((unsigned)((a.nq + 7) / 8), (unsigned)splits);
+    const int64_t total = a.tiles * a.splits;
+    const unsigned grid = (unsigned)std::min<int64_t>(total, num_sms());
     kern<<<grid, CF_THREADS, smem, st>>>(a);
     RC_CHECK_LAUNCH("adc_scan_cf_kernel");
     return RC_OK;
+}
+
+// items: splits of ~32k documents (at least ~32 items per CTA when the corpus allows, never more than 8 MB of codes
+// so that a split stays L2-resident while the query tiles sweep over it)
+static int launch_cf(PackScanArgs a, bool sample, cudaStream_t st) {
+    if (a.nq <= 0 || a.npos <= 0) return RC_OK;
+    const int qp = cf_qp(a.M);
+    const int docs_per_it = qp == 8 ? 128 : 64;
+    a.tiles = (a.nq + qp - 1) / qp;
+    int64_t pps = (32 * (int64_t)num_sms() + a.tiles - 1) / a.tiles;        // splits wanted
+    pps = (a.npos + pps - 1) / pps;                                          // -> positions per split
+    pps = std::min<int64_t>(pps, (8 << 20) / a.M);
+    pps = std::max<int64_t>(pps, 16384);
+    pps = (pps + docs_per_it - 1) / docs_per_it * docs_per_it;
+    a.pos_per_split = pps;
+    a.splits = (a.npos + pps - 1) / pps;
+    if (sample) RC_CUDA(cudaMemsetAsync(a.item_ctr, 0, 4, st));
+    // LSU wavefronts of this launch (what ncu counts as l1tex__data_pipe_lsu_wavefronts)
+    if (!sample) {
+        const double per_group = qp == 8 ? a.M / 2.0 + 6.0 : a.M / 8.0 + 5.0;   // gathers + exchange + code bytes
+        g_scan_wavefronts += (double)a.tiles * ((double)a.npos / (qp == 8 ? 4.0 : 2.0)) * per_group;
+        g_scan_kernel = qp == 8 ? "adc_scan_cf_kernel<8 queries/entry>" : "adc_scan_cf_kernel<4 queries/entry>";
+    }
+#define RC_CF(MT, QP)                                                        \
+    case MT: return sample ? launch_cf_inst<MT, QP, true>(a, st) : launch_cf_inst<MT, QP, false>(a, st)
+    if (qp == 8) {
+        switch (a.M) {
+            RC_CF(8, 8); RC_CF(16, 8); RC_CF(24, 8); RC_CF(32, 8); RC_CF(40, 8); RC_CF(48, 8);
+            default: break;
+        }
+    } else {
+        switch (a.M) {
+            RC_CF(64, 4); RC_CF(80, 4); RC_CF(96, 4);
+            default: break;
+        }
+    }
+#undef RC_CF
+    set_error("launch_cf: unsupported M=%d", a.M);
+    return RC_E_UNSUPPORTED;
 }
 
 // r-th largest 16-bit integer sum of a sample row (2 radix passes); the filter threshold of the packed scan
@@ -503,30 +701,6 @@ radix_select_u16_kernel(const uint16_t* __restrict__ dense, int64_t ld, int64_t 
         }
         thr_i[q] = (int)((hi << 8) | (unsigned int)b);
     }
-}
-
-static void scan_splits(int64_t nq, int qt, int64_t npos, int M, int64_t* pps_out, int64_t* splits_out);
-
-// true when the conflict-free kernel (and with it the integer-domain sampling) serves this M
-static bool cf_capable(int M) { return M % 8 == 0 && M >= 8 && M <= 48; }
-
-static int launch_cf_sample(PackScanArgs a, cudaStream_t st) {
-    int64_t pps, splits;
-    scan_splits(a.nq, 8, a.npos, a.M, &pps, &splits);
-    pps = (pps + 127) / 128 * 128;
-    splits = (a.npos + pps - 1) / pps;
-    a.pos_per_split = pps;
-    switch (a.M) {
-        case 8: return launch_cf_inst<8, true>(a, (int)splits, st);
-        case 16: return launch_cf_inst<16, true>(a, (int)splits, st);
-        case 24: return launch_cf_inst<24, true>(a, (int)splits, st);
-        case 32: return launch_cf_inst<32, true>(a, (int)splits, st);
-        case 40: return launch_cf_inst<40, true>(a, (int)splits, st);
-        case 48: return launch_cf_inst<48, true>(a, (int)splits, st);
-        default: break;
-    }
-    set_error("launch_cf_sample: unsupported M=%d", a.M);
-    return RC_E_UNSUPPORTED;
 }
 
 static int scan_qp(int M) {
@@ -591,29 +765,10 @@ static int launch_packed(PackScanArgs a, cudaStream_t st) {
     scan_splits(a.nq, qp, a.npos, a.M, &pps, &splits);
     a.pos_per_split = pps;
 #define RC_PSCAN(QP, MT) return launch_packed_inst<QP, MT>(a, (int)splits, st)
-    // LSU wavefronts of this launch (what ncu counts as l1tex__data_pipe_lsu_wavefronts): per warp and group of
-    // 4 documents x 8 queries the conflict-free kernel issues M/8 LDS.128 (4 wavefronts each), 4 exchange
-    // shuffles and 2 wavefronts of code bytes; the thread-per-document gather issues one 16 / 8 / 4-byte gather
-    // per (document, sub-vector) per tile at the measured 2.5 conflict wavefronts per ideal wavefront
-    const double tiles = (double)((a.nq + qp - 1) / qp);
-    if (qp == 8 && cf_capable(a.M) && !adc_force_gather()) {
-        g_scan_wavefronts += tiles * ((double)a.npos / 4.0) * (a.M / 2.0 + 6.0);
-        g_scan_kernel = "adc_scan_cf_kernel";
-    } else {
-        g_scan_wavefronts += tiles * ((double)a.npos / 32.0) * a.M * (qp * 2 / 4.0) * 2.5;
-        g_scan_kernel = "adc_scan_packed_kernel";
-    }
-    if (qp == 8 && !adc_force_gather()) {
-        switch (a.M) {   // conflict-free layout
-            case 8: return launch_cf_inst<8>(a, (int)splits, st);
-            case 16: return launch_cf_inst<16>(a, (int)splits, st);
-            case 24: return launch_cf_inst<24>(a, (int)splits, st);
-            case 32: return launch_cf_inst<32>(a, (int)splits, st);
-            case 40: return launch_cf_inst<40>(a, (int)splits, st);
-            case 48: return launch_cf_inst<48>(a, (int)splits, st);
-            default: break;
-        }
-    }
+    // LSU wavefronts: one 16 / 8 / 4-byte gather per (document, sub-vector) per tile at the measured 2.5 conflict
+    // wavefronts per ideal wavefront
+    g_scan_wavefronts += (double)((a.nq + qp - 1) / qp) * ((double)a.npos / 32.0) * a.M * (qp * 2 / 4.0) * 2.5;
+    g_scan_kernel = "adc_scan_packed_kernel";
     if (qp == 8) {
         switch (a.M) {
             case 8: RC_PSCAN(8, 8);
@@ -1005,6 +1160,7 @@ struct AdcWs {
     unsigned int* count_gt; int* status; float* fb_lut; float* fb_scores; int64_t* fb_ids;
     uint16_t* qlut; float* qstep; double* qsumlo; double* qsumabs; int* thr_i; uint32_t* cand32;
     unsigned int* exact_cnt;
+    unsigned int* item_ctr;      // 2 work-item counters (sample scan, corpus scan)
 };
 
 static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPlan& p, void* base, AdcWs* w) {
@@ -1027,14 +1183,16 @@ static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPl
     const size_t o_fl = take((size_t)FB_ROWS * M * ADC_K * 4);
     const size_t o_fs = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 4);
     const size_t o_fi = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 8);
-    const size_t o_ql = take((size_t)qc * M * ADC_K * 2);
+    const size_t o_ql = take((size_t)((qc + 7) / 8 * 8) * M * ADC_K * 2);      // whole tiles of 8 / 4 queries
     const size_t o_qs = take((size_t)qc * 4);
     const size_t o_qo = take((size_t)qc * 8);
     const size_t o_qa = take((size_t)qc * 8);
     const size_t o_ti = take((size_t)qc * 4);
     const size_t o_c32 = take((size_t)qc * CAND_CAP * 4);
     const size_t o_ec = take((size_t)qc * 4);
+    const size_t o_ic = take(16);
     if (w) {
+        w->item_ctr = (unsigned int*)(b + o_ic);
         w->qlut = (uint16_t*)(b + o_ql);
         w->qstep = (float*)(b + o_qs);
         w->qsumlo = (double*)(b + o_qo);
@@ -1188,8 +1346,33 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
     const int64_t chunk = std::min<int64_t>(Q_CHUNK, ((nq + n_chunks - 1) / n_chunks + 7) / 8 * 8);
     for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
         const int64_t qc = std::min<int64_t>(chunk, nq - c0);
-        rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
-        if (rc) return rc;
+        const int qmax = 65535 / M;
+        const bool int_sampling = !p.dense_all && cf_capable(M) && !adc_force_gather();
+        if (int_sampling) {
+            // fp32 tables + integer tables in the scan's shared-memory layout, one kernel
+            const int qp = cf_qp(M);
+            const unsigned tiles = (unsigned)((qc + qp - 1) / qp);
+            const size_t sm = ((size_t)qp * M * ds + (size_t)qp * M + 8 * qp * 2 + qp) * 4;
+            static unsigned long long attr_seen = 0ull;
+            if (first_use_on_device(attr_seen)) {
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            }
+            if (sm > 160 * 1024) {
+                set_error("rc_adc_search: query dimension %d too large for the table builder", M * ds);
+                return RC_E_UNSUPPORTED;
+            }
+            if (qp == 8)
+                adc_lut_pack_kernel<8><<<tiles, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, w.lut,
+                                                               w.qlut, w.qstep, w.qsumlo, w.qsumabs);
+            else
+                adc_lut_pack_kernel<4><<<tiles, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, w.lut,
+                                                               w.qlut, w.qstep, w.qsumlo, w.qsumabs);
+            RC_CHECK_LAUNCH("adc_lut_pack_kernel");
+        } else {
+            rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
+            if (rc) return rc;
+        }
         if (p.dense_all) {
             for (int64_t r0 = 0; r0 < qc; r0 += p.dense_rows) {
                 const int rows = (int)std::min<int64_t>(p.dense_rows, qc - r0);
@@ -1204,11 +1387,11 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             g_stats[1] += qc;
             continue;
         }
-        const int qmax = 65535 / M;
-        adc_quantise_lut_kernel<<<(unsigned)qc, ADC_K, (size_t)M * 4, st>>>(w.lut, M, qmax, w.qlut, w.qstep, w.qsumlo,
-                                                                          w.qsumabs);
-        RC_CHECK_LAUNCH("adc_quantise_lut_kernel");
-        const bool int_sampling = cf_capable(M) && !adc_force_gather();
+        if (!int_sampling) {
+            adc_quantise_lut_kernel<<<(unsigned)qc, ADC_K, (size_t)M * 4, st>>>(w.lut, M, qmax, w.qlut, w.qstep, w.qsumlo,
+                                                                              w.qsumabs);
+            RC_CHECK_LAUNCH("adc_quantise_lut_kernel");
+        }
         // 1. thresholds from a strided sample of the corpus
         if (int_sampling) {
             // integer domain: the sample is scanned by the packed kernel itself and the threshold is the
@@ -1217,7 +1400,8 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             a.qlut = w.qlut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.M = M;
             a.blk = SAMPLE_BLK; a.stride = p.stride; a.out16 = reinterpret_cast<uint16_t*>(w.dense);
             a.ld16 = p.n_sample;
-            rc = launch_cf_sample(a, st);
+            a.item_ctr = w.item_ctr;
+            rc = launch_cf(a, true, st);
             if (rc) return rc;
             radix_select_u16_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(reinterpret_cast<uint16_t*>(w.dense),
                                                                            p.n_sample, p.n_sample, p.rank_sample,
@@ -1242,8 +1426,10 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             PackScanArgs a{};
             a.qlut = w.qlut; a.codes = codes; a.thr_i = w.thr_i; a.nq = qc; a.npos = N; a.M = M;
             a.cnt = w.cnt; a.cand = w.cand32; a.cap = CAND_CAP;
+            a.item_ctr = w.item_ctr + 1;
+            if (int_sampling) RC_CUDA(cudaMemsetAsync(a.item_ctr, 0, 4, st));   // (outside the timed region)
             if (ev0) RC_CUDA(cudaEventRecord(ev0, st));
-            rc = launch_packed(a, st);
+            rc = int_sampling ? launch_cf(a, false, st) : launch_packed(a, st);
             if (rc) return rc;
             if (ev1) RC_CUDA(cudaEventRecord(ev1, st));
         }

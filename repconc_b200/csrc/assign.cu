@@ -258,26 +258,6 @@ constexpr int SK_THREADS = SK_WARPS * 32;
 constexpr int SK_CTAS_PER_SM = 2;
 constexpr int SK_DEPTH = 4;  // table rows in flight per warp (TMA ring)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 // Programmatic dependent launch: the kernels of the solve loop are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled while this one
 // drains.  Every such kernel calls pdl_wait() before it touches anything a predecessor wrote (or may still
