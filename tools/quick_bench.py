@@ -32,7 +32,7 @@ if "assign" in what:
               f"{M * B * 256 * 4 / per_pass / 1e6:.0f} GB/s", flush=True)
 if "adc" in what:
     N = int(os.environ.get("QB_N", 8841823))
-    for (M, nq, k) in [(48, 1024, 1000), (32, 1024, 1000), (48, 128, 200)]:
+    for (M, nq, k) in [(48, 1200, 1000), (32, 1200, 1000), (64, 1200, 1000), (96, 1200, 1000), (48, 128, 200)]:
         ds = 768 // M
         codes = torch.randint(0, 256, (N, M), generator=gen, device="cuda", dtype=torch.uint8)
         c = torch.randn((M, 256, ds), generator=gen, device="cuda")
