@@ -37,6 +37,7 @@ constexpr int ADC_K = 256;
 constexpr int SCAN_THREADS = 512;
 constexpr int SEL_THREADS = 1024;
 constexpr int CAND_CAP = 8192;        // candidate list capacity per query == max sortable k
+constexpr int CAND_CAP32 = 32768;    // capacity of the integer filter's list (document positions, re-scored exactly)
 constexpr int Q_CHUNK = 2048;         // max queries processed per pass of the host loop
 constexpr int FB_ROWS = 4;            // exact-fallback queries per dense scan
 constexpr int64_t DENSE_N_MAX = 262144;  // corpora up to this size take the dense path
@@ -359,72 +360,102 @@ adc_scan_packed_kernel(PackScanArgs a) {
 // Replaces adc_lut_kernel (0.44 ms per 1200 queries: one CTA per (query, sub-vector), every centroid re-read
 // per query) + adc_quantise_lut_kernel (0.09 ms).
 // ---------------------------------------------------------------------------------------------
-template <int QP>
-__global__ void __launch_bounds__(256)
+// (declared here, defined with the 8-bit scan) table position of sub-vector m in a tile of 8-bit fields
+__host__ __device__ inline int u8_pos(int m, int M, int eb, int lpd);
+
+// U8 = false: 16-bit fields, entry = QP * 2 bytes at position m;  U8 = true: 8-bit fields, entry = QP bytes at
+// position u8_pos(m) (adc_scan_u8_kernel with `lpd` lanes per document)
+constexpr int LP_THREADS = 1024;   // 4 groups of 256 threads (thread = centroid k), group g takes sub-vectors m = g, g + 4, ...
+constexpr int LP_GROUPS = LP_THREADS / 256;
+
+template <int QP, bool U8>
+__global__ void __launch_bounds__(LP_THREADS)
 adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float* __restrict__ c, int64_t nq, int M,
-                    int ds, int qmax, float* __restrict__ lut, uint16_t* __restrict__ qpack,
+                    int ds, int qmax, int lpd, float* __restrict__ lut, uint16_t* __restrict__ qpack,
                     float* __restrict__ step_out, double* __restrict__ sumlo_out, double* __restrict__ sumabs_out) {
     extern __shared__ __align__(16) float lp_sh[];
     const int D = M * ds;
-    float* qs = lp_sh;                         // [QP][D]
-    float* q_lo = qs + QP * D;                 // [QP][M]
-    float* red = q_lo + QP * M;                // [8 warps][QP][2]
-    float* s_step = red + 8 * QP * 2;          // [QP]
+    float* qs = lp_sh;                         // [D][QP]  (the QP queries of a dimension are contiguous: vector reads)
+    float* wred = qs + QP * D;                 // [M][8 warps of the group][QP][2]  per-warp min / max
+    float* q_lo = wred + (size_t)M * 8 * QP * 2;   // [QP][M]
+    float* q_hi = q_lo + QP * M;               // [QP][M]
+    float* s_step = q_hi + QP * M;             // [QP]
     const int64_t tile = blockIdx.x;
     const int64_t q0 = tile * QP;
     const int nqt = (int)min((int64_t)QP, nq - q0);
-    const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
-    for (int i = k; i < QP * D; i += 256) {
+    const int g = threadIdx.x >> 8, k = threadIdx.x & 255, lane = k & 31, warp = k >> 5;
+    for (int i = threadIdx.x; i < QP * D; i += LP_THREADS) {
         const int qq = i / D, d = i - qq * D;
-        qs[i] = qq < nqt ? queries[(q0 + qq) * ldq + d] : 0.0f;
+        qs[d * QP + qq] = qq < nqt ? queries[(q0 + qq) * ldq + d] : 0.0f;
     }
     __syncthreads();
-    float range = 0.0f;                        // thread qq < QP tracks its query
-    double sumabs = 0.0, sumlo = 0.0;
-    for (int m = 0; m < M; ++m) {
+    for (int m = g; m < M; m += LP_GROUPS) {
         const float* ck = c + ((int64_t)m * ADC_K + k) * ds;
         float sacc[QP];
 #pragma unroll
         for (int qq = 0; qq < QP; ++qq) sacc[qq] = 0.0f;
         for (int j = 0; j < ds; ++j) {
             const float cj = __ldg(ck + j);
+            const float4* qv = reinterpret_cast<const float4*>(qs + (size_t)(m * ds + j) * QP);
 #pragma unroll
-            for (int qq = 0; qq < QP; ++qq) sacc[qq] = __fadd_rn(sacc[qq], __fmul_rn(qs[qq * D + m * ds + j], cj));
+            for (int v = 0; v < QP / 4; ++v) {
+                const float4 x = qv[v];
+                sacc[4 * v + 0] = __fadd_rn(sacc[4 * v + 0], __fmul_rn(x.x, cj));
+                sacc[4 * v + 1] = __fadd_rn(sacc[4 * v + 1], __fmul_rn(x.y, cj));
+                sacc[4 * v + 2] = __fadd_rn(sacc[4 * v + 2], __fmul_rn(x.z, cj));
+                sacc[4 * v + 3] = __fadd_rn(sacc[4 * v + 3], __fmul_rn(x.w, cj));
+            }
         }
 #pragma unroll
         for (int qq = 0; qq < QP; ++qq) {
             if (qq < nqt) lut[((q0 + qq) * M + m) * ADC_K + k] = sacc[qq];
             const float lo = warp_min(sacc[qq]), hi = warp_max(sacc[qq]);
-            if (lane == 0) { red[(warp * QP + qq) * 2] = lo; red[(warp * QP + qq) * 2 + 1] = hi; }
+            if (lane == 0) {
+                wred[((m * 8 + warp) * QP + qq) * 2] = lo;
+                wred[((m * 8 + warp) * QP + qq) * 2 + 1] = hi;
+            }
         }
-        __syncthreads();
-        if (k < QP) {
-            float l = red[k * 2], h = red[k * 2 + 1];
-            for (int w = 1; w < 8; ++w) { l = fminf(l, red[(w * QP + k) * 2]); h = fmaxf(h, red[(w * QP + k) * 2 + 1]); }
-            q_lo[k * M + m] = l;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QP * M; i += LP_THREADS) {
+        const int qq = i / M, m = i - qq * M;
+        float l = wred[((m * 8) * QP + qq) * 2], h = wred[((m * 8) * QP + qq) * 2 + 1];
+        for (int w = 1; w < 8; ++w) {
+            l = fminf(l, wred[((m * 8 + w) * QP + qq) * 2]);
+            h = fmaxf(h, wred[((m * 8 + w) * QP + qq) * 2 + 1]);
+        }
+        q_lo[i] = l;
+        q_hi[i] = h;
+    }
+    __syncthreads();
+    if (threadIdx.x < QP) {
+        const int qq = threadIdx.x;
+        float range = 0.0f;
+        double sumabs = 0.0, sumlo = 0.0;
+        for (int m = 0; m < M; ++m) {
+            const float l = q_lo[qq * M + m], h = q_hi[qq * M + m];
             range = fmaxf(range, h - l);
             sumabs += (double)fmaxf(fabsf(l), fabsf(h));
             sumlo += (double)l;
         }
-        __syncthreads();
-    }
-    if (k < QP) {
         // a degenerate (constant) table still needs a positive step
         const float step = fmaxf(range, 1e-30f) / (float)qmax;
-        s_step[k] = step;
-        if (k < nqt) {
-            step_out[q0 + k] = step;
-            sumlo_out[q0 + k] = sumlo;
-            sumabs_out[q0 + k] = sumabs;
+        s_step[qq] = step;
+        if (qq < nqt) {
+            step_out[q0 + qq] = step;
+            sumlo_out[q0 + qq] = sumlo;
+            sumabs_out[q0 + qq] = sumabs;
         }
     }
     __syncthreads();
-    // second sweep: quantise this thread's own column k of every (query, sub-vector) and write the entries
-    uint16_t* tp = qpack + (size_t)tile * M * ADC_K * QP;
-    for (int m = 0; m < M; ++m) {
-        uint32_t w[QP / 2];
+    // second sweep: quantise this thread's own column k of every (query, sub-vector) of its group and write the entries
+    constexpr int FB = U8 ? 1 : 2;              // bytes per field
+    constexpr int NW = QP * FB / 4;             // words per entry
+    unsigned char* tp = reinterpret_cast<unsigned char*>(qpack) + (size_t)tile * M * ADC_K * QP * FB;
+    for (int m = g; m < M; m += LP_GROUPS) {
+        uint32_t w[NW];
 #pragma unroll
-        for (int i = 0; i < QP / 2; ++i) w[i] = 0u;
+        for (int i = 0; i < NW; ++i) w[i] = 0u;
 #pragma unroll
         for (int qq = 0; qq < QP; ++qq) {
             int qi = 0;
@@ -433,10 +464,12 @@ adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float*
                 qi = __float2int_rn((v - q_lo[qq * M + m]) / s_step[qq]);
                 qi = qi < 0 ? 0 : (qi > qmax ? qmax : qi);
             }
-            w[qq >> 1] |= (uint32_t)qi << (16 * (qq & 1));
+            if constexpr (U8) w[qq >> 2] |= (uint32_t)qi << (8 * (qq & 3));
+            else w[qq >> 1] |= (uint32_t)qi << (16 * (qq & 1));
         }
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tp + ((size_t)k * M + m) * QP);
-        if constexpr (QP == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        const int pos = U8 ? u8_pos(m, M, QP, lpd) : m;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tp + ((size_t)k * M + pos) * (QP * FB));
+        if constexpr (NW == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
         else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
     }
 }
@@ -660,6 +693,387 @@ static int launch_cf(PackScanArgs a, bool sample, cudaStream_t st) {
 #undef RC_CF
     set_error("launch_cf: unsupported M=%d", a.M);
     return RC_E_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 8-bit-field filter scan: TWICE the queries per shared-memory byte.  adc_scan_cf_kernel sits on the LSU wavefront
+// limit (ncu: 98 % of peak, issue 53 %), so the only way up is fewer shared-memory bytes per (document, query,
+// sub-vector): here a table entry carries one BYTE per query (16 queries per 16-byte entry for M <= 48, 8 queries per
+// 8-byte entry for M = 64 / 80 / 96 whose tables would not fit otherwise), four queries per 32-bit word.
+//   * arithmetic: ACC8 consecutive entries of a lane are added as packed bytes (q <= QMAX = 255 / ACC8, no carry
+//     between the byte fields; three entries are one IADD3), then widened to two words of 16-bit fields (PRMT) and
+//     accumulated there; the cross-lane reduction is the halving exchange of the 16-bit kernel.  The coarser
+//     quantisation only widens the candidate set: a document is kept when its integer sum reaches
+//     T = S_r - ceil(0.501 M + slack) - 1 (S_r: r-th largest sum of the sample), the exact re-score then keeps what
+//     is strictly above the largest exact score an excluded document can have -- same exactness argument as before.
+//   * geometry: LPD lanes per document (8 or 4), each with NE = M / LPD CONSECUTIVE code bytes (one vector load
+//     instead of NE byte loads).  Sub-vector m = NE*j + i (lane j, byte i) lives at table position
+//     pos = BG*(i / DPP) + LPD*(i % DPP) + j   (BG = 128 / entry bytes = entries per 128-byte wavefront,
+//     DPP = BG / LPD = documents that share a shared-memory phase), and document slot s of a phase walks its bytes in
+//     the order i = t ^ s, so that at every step the BG lanes of a phase hit BG different bank groups whatever the
+//     codes are: conflict-free with 4 lanes per document too (half the exchange steps per document).
+// Work distribution, table staging (bulk copies of tiles already written in this layout by adc_lut_pack_kernel) and
+// sample mode are those of adc_scan_cf_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// table position of sub-vector m (host + device)
+__host__ __device__ inline int u8_pos(int m, int M, int eb, int lpd) {
+    const int bg = 128 / eb, dpp = bg / lpd, ne = M / lpd;
+    const int j = m / ne, i = m % ne;
+    return bg * (i / dpp) + lpd * (i % dpp) + j;
+}
+
+template <int N>
+__device__ __forceinline__ void u8_halve(uint32_t* w, bool hi, int d) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const uint32_t send = hi ? w[i] : w[N / 2 + i];
+        const uint32_t keep = hi ? w[N / 2 + i] : w[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+    }
+}
+
+// reduction over the lanes of a document: exchange distance D, D/2, ... 1; halve the word set while more than NWF
+// words are left, plain butterflies afterwards
+template <int N, int D, int NWF>
+__device__ __forceinline__ void u8_reduce(uint32_t* w, int j) {
+    if constexpr (D >= 1) {
+        if constexpr (N > NWF) {
+            u8_halve<N>(w, (j & D) != 0, D);
+            u8_reduce<N / 2, D / 2, NWF>(w, j);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) w[i] += __shfl_xor_sync(0xffffffffu, w[i], D);
+            u8_reduce<N, D / 2, NWF>(w, j);
+        }
+    }
+}
+
+template <int MT, int EB, int LPD, int ACC8, bool SAMPLE>
+__global__ void __launch_bounds__(CF_THREADS, 1)
+adc_scan_u8_kernel(PackScanArgs a) {
+    static_assert(EB == 16 || EB == 8, "16 or 8 queries per entry");
+    static_assert(LPD == 8 || LPD == 4 || LPD == 2, "8, 4 or 2 lanes per document");
+    static_assert(128 / EB / LPD <= 4, "the byte permutation of a document slot stays inside a 32-bit word");
+    constexpr int BG = 128 / EB, DPP = BG / LPD, NE = MT / LPD, DPW = 32 / LPD;
+    static_assert(MT % BG == 0, "whole phases");
+    constexpr int DOCS_PER_IT = (CF_THREADS / 32) * DPW;
+    constexpr int NW8 = EB / 4, NW16 = EB / 2;
+    constexpr int LOG_LPD = LPD == 8 ? 3 : LPD == 4 ? 2 : 1, LOG_NW16 = NW16 == 8 ? 3 : 2;
+    constexpr int HSTEPS = LOG_LPD < LOG_NW16 ? LOG_LPD : LOG_NW16;   // halving steps, then butterflies
+    constexpr int NWF = NW16 >> HSTEPS;                               // words a lane ends up with
+    constexpr int RSH = LPD >> HSTEPS;                                // lanes that end up with the same word (1 or 2)
+    constexpr int AL = (NE % 8 == 0) ? 8 : (NE % 4 == 0) ? 4 : (NE % 2 == 0) ? 2 : 1;   // code load width
+    constexpr int NU = NE / AL, NCW = (NE + 3) / 4;
+    constexpr int NUR = AL == 8 ? NE / 4 : NU;            // registers holding the loaded code bytes
+    constexpr uint32_t TILE_BYTES = (uint32_t)MT * ADC_K * EB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_BYTES);
+    int* s_item = reinterpret_cast<int*>(smem_raw + TILE_BYTES + 8);
+    const uint32_t bar_a = smem_u32(bar);
+    const uint32_t lut_a = smem_u32(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & (LPD - 1), sub = lane / LPD, slot = sub & (DPP - 1);
+    // per-lane table bases: step t reads  base[t % DPP] + 128 * (t / DPP) + code * MT * EB
+    uint32_t base[DPP];
+#pragma unroll
+    for (int r = 0; r < DPP; ++r) base[r] = lut_a + (uint32_t)EB * (uint32_t)(LPD * (r ^ slot) + j);
+    const uint32_t perm_sel = 0x3210u ^ (0x1111u * (uint32_t)slot);   // byte t of the permuted word = byte t ^ slot
+    if (threadIdx.x == 0) mbar_init(bar_a, 1);
+    fence_barrier_init();
+    __syncthreads();
+    const int64_t total = a.tiles * a.splits;
+    int64_t cur_tile = -1;
+    uint32_t phase = 0;
+    int64_t q0 = 0;
+    int nqt = 0;
+    // the queries this lane tests: final word x = widx * NWF + f holds queries 4 (x >> 1) + (x & 1) [low 16 bits] and
+    // + 2 [high 16 bits]; with RSH == 2 the two lanes that share a word test one field each
+    const int widx = j >> (LOG_LPD - HSTEPS);
+    uint32_t bias[NWF];          // packed (0x8000 - threshold) per field: field >= threshold <=> bit 15 of field + bias
+#pragma unroll
+    for (int f = 0; f < NWF; ++f) bias[f] = 0u;
+
+    for (;;) {
+        if (threadIdx.x == 0) *s_item = (int)atomicAdd(a.item_ctr, 1u);
+        __syncthreads();                                  // (also: every gather of the previous item has been consumed)
+        const int64_t item = *s_item;
+        __syncthreads();                                  // s_item is rewritten by the next fetch
+        if (item >= total) break;
+        const int64_t tile = item % a.tiles, split = item / a.tiles;
+        if (tile != cur_tile) {
+            if (threadIdx.x == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar_a, TILE_BYTES);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)tile * TILE_BYTES;
+                for (uint32_t o = 0; o < TILE_BYTES; o += 32768u)
+                    bulk_load(smem_raw + o, src + o, min(32768u, TILE_BYTES - o), bar_a);
+            }
+            q0 = tile * EB;
+            nqt = (int)min((int64_t)EB, a.nq - q0);
+            if (!SAMPLE) {
+#pragma unroll
+                for (int f = 0; f < NWF; ++f) {
+                    const int x = widx * NWF + f;
+                    const int qa = 4 * (x >> 1) + (x & 1), qb = qa + 2;
+                    // thresholds above 0x8000 cannot be reached (M * QMAX <= 24480): 0x8000 keeps the bias in range
+                    const int ta = qa < nqt ? min(a.thr_i[q0 + qa], 0x8000) : 0x8000;
+                    const int tb = qb < nqt ? min(a.thr_i[q0 + qb], 0x8000) : 0x8000;
+                    bias[f] = (uint32_t)(0x8000 - ta) | ((uint32_t)(0x8000 - tb) << 16);
+                }
+            }
+            mbar_wait(bar_a, phase);
+            phase ^= 1u;
+            cur_tile = tile;
+        }
+        const int64_t p_lo = split * a.pos_per_split;
+        const int64_t p_hi = min(a.npos, p_lo + a.pos_per_split);
+
+        // one group of DPW documents: gather, exchange over the document's lanes, threshold test
+        auto scan_group = [&](const uint32_t (&cu)[NUR], int64_t p, bool live) {
+            // code bytes as words, in the order this document slot walks them
+            uint32_t cw[NCW];
+            if constexpr (AL == 8) {
+#pragma unroll
+                for (int i = 0; i < NCW; ++i) cw[i] = cu[i];     // (cu already holds 32-bit halves, see the loads)
+            } else if constexpr (AL == 4) {
+#pragma unroll
+                for (int i = 0; i < NCW; ++i) cw[i] = cu[i];
+            } else if constexpr (AL == 2) {
+#pragma unroll
+                for (int i = 0; i < NCW; ++i) cw[i] = cu[2 * i] | ((2 * i + 1 < NU ? cu[2 * i + 1] : 0u) << 16);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NCW; ++i) {
+                    uint32_t w = 0u;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (4 * i + b < NU) w |= cu[4 * i + b] << (8 * b);
+                    cw[i] = w;
+                }
+            }
+            if constexpr (DPP > 1) {
+#pragma unroll
+                for (int i = 0; i < NCW; ++i) cw[i] = prmt(cw[i], 0u, perm_sel);
+            }
+            uint32_t acc16[NW16];
+#pragma unroll
+            for (int i = 0; i < NW16; ++i) acc16[i] = 0u;
+#pragma unroll
+            for (int t0 = 0; t0 < NE; t0 += ACC8) {
+                uint32_t acc8[NW8];
+#pragma unroll
+                for (int i = 0; i < NW8; ++i) acc8[i] = 0u;
+#pragma unroll
+                for (int t = t0; t < t0 + ACC8 && t < NE; ++t) {
+                    const uint32_t code = (cw[t >> 2] >> (8 * (t & 3))) & 0xffu;
+                    const uint32_t addr = base[t % DPP] + 128u * (uint32_t)(t / DPP) + code * (uint32_t)(MT * EB);
+                    if constexpr (EB == 16) {
+                        const uint4 v = lds_v4(addr);
+                        acc8[0] += v.x; acc8[1] += v.y; acc8[2] += v.z; acc8[3] += v.w;
+                    } else {
+                        const uint2 v = lds_v2(addr);
+                        acc8[0] += v.x; acc8[1] += v.y;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NW8; ++i) {
+                    acc16[2 * i] += prmt(acc8[i], 0u, 0x4240u);       // bytes 0, 2 -> 16-bit fields
+                    acc16[2 * i + 1] += prmt(acc8[i], 0u, 0x4341u);   // bytes 1, 3
+                }
+            }
+            // reduce over the LPD lanes of the document: halve the word set while more than NWF words are left
+            u8_reduce<NW16, LPD / 2, NWF>(acc16, j);
+#pragma unroll
+            for (int f = 0; f < NWF; ++f) {
+                const uint32_t w = acc16[f];
+                const int x = widx * NWF + f;
+                const int qa = 4 * (x >> 1) + (x & 1), qb = qa + 2;
+                if (SAMPLE) {
+                    if (live) {
+                        if (RSH == 1 || (j & 1) == 0) {
+                            if (qa < nqt) a.out16[(q0 + qa) * a.ld16 + p] = (uint16_t)(w & 0xffffu);
+                        }
+                        if (RSH == 1 || (j & 1) == 1) {
+                            if (qb < nqt) a.out16[(q0 + qb) * a.ld16 + p] = (uint16_t)(w >> 16);
+                        }
+                    }
+                } else {
+                    uint32_t hit = (w + bias[f]) & 0x80008000u;
+                    if (RSH == 2) hit &= (j & 1) ? 0x80000000u : 0x00008000u;
+                    if (hit != 0u && live) {
+                        if (hit & 0x8000u) {
+                            const unsigned int pos = atomicAdd(a.cnt + q0 + qa, 1u);
+                            if (pos < (unsigned int)a.cap) a.cand[(q0 + qa) * (int64_t)a.cap + pos] = (uint32_t)p;
+                        }
+                        if (hit & 0x80000000u) {
+                            const unsigned int pos = atomicAdd(a.cnt + q0 + qb, 1u);
+                            if (pos < (unsigned int)a.cap) a.cand[(q0 + qb) * (int64_t)a.cap + pos] = (uint32_t)p;
+                        }
+                    }
+                }
+            }
+        };
+        // position -> this lane's NE code bytes (sample mode scans evenly spaced blocks of the corpus)
+        auto code_ptr = [&](int64_t pos) {
+            const int64_t doc = SAMPLE ? (pos / a.blk) * a.stride + (pos % a.blk) : pos;
+            return a.codes + doc * MT + NE * j;
+        };
+        auto load_codes = [&](const uint8_t* cp, uint32_t (&cu)[NUR]) {
+            if constexpr (AL == 8) {
+#pragma unroll
+                for (int i = 0; i < NE / 8; ++i) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp) + i);
+                    cu[2 * i] = v.x; cu[2 * i + 1] = v.y;
+                }
+            } else if constexpr (AL == 4) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) cu[i] = __ldg(reinterpret_cast<const uint32_t*>(cp) + i);
+            } else if constexpr (AL == 2) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) cu[i] = __ldg(reinterpret_cast<const uint16_t*>(cp) + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) cu[i] = __ldg(cp + i);
+            }
+        };
+        const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
+        int64_t p = p_lo + warp * DPW + sub;
+        const uint8_t* cp = code_ptr(p);
+        uint32_t cb[NUR], cn[NUR];
+        if (full > 0) load_codes(cp, cb);
+        for (int64_t t = 0; t < full; ++t) {
+            if (t + 1 < full) load_codes(SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT, cn);
+            scan_group(cb, p, true);
+#pragma unroll
+            for (int i = 0; i < NUR; ++i) cb[i] = cn[i];
+            p += DOCS_PER_IT;
+            cp += (int64_t)DOCS_PER_IT * MT;
+        }
+        // tail: fewer than DOCS_PER_IT documents left in the split
+        if (p_lo + full * DOCS_PER_IT < p_hi) {   // block-uniform
+            const bool live = p < p_hi;
+            if (live) {
+                load_codes(code_ptr(p), cb);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NUR; ++i) cb[i] = 0u;
+            }
+            scan_group(cb, p, live);
+        }
+    }
+}
+
+// which 8-bit-field variant serves this M: entry bytes = queries per tile (16, 8) or 0 (none)
+static int u8_eb(int M) {
+    if (M % 8 == 0 && M >= 8 && M <= 48) return 16;
+    if (M % 16 == 0 && M <= 96) return 8;
+    return 0;
+}
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+// lanes per document and entries added in 8-bit fields before widening (QMAX = 255 / acc); RC_ADC_U8_LPD / RC_ADC_U8_ACC
+// select another compiled variant for A/B measurements
+struct U8Cfg { int eb, lpd, acc; };
+static U8Cfg u8_cfg(int M) {
+    U8Cfg c{u8_eb(M), 8, 2};
+    static const int e_lpd = env_int("RC_ADC_U8_LPD", 0), e_acc = env_int("RC_ADC_U8_ACC", 0);
+    if (M == 48 || M == 32 || M == 64 || M == 96) {
+        c.lpd = M == 32 ? 2 : 4;
+        if (e_lpd) c.lpd = e_lpd;
+        if (e_acc) c.acc = e_acc;
+    }
+    return c;
+}
+// RC_ADC_FIELDS=16 keeps the 16-bit-field scan (adc_scan_cf_kernel) for A/B measurements
+static bool u8_enabled(int M) {
+    static const int fields = env_int("RC_ADC_FIELDS", 8);
+    return fields != 16 && u8_eb(M) != 0;
+}
+
+template <int MT, int EB, int LPD, int ACC8, bool SAMPLE>
+static int launch_u8_inst(const PackScanArgs& a, cudaStream_t st) {
+    auto kern = adc_scan_u8_kernel<MT, EB, LPD, ACC8, SAMPLE>;
+    const size_t smem = (size_t)MT * ADC_K * EB + 16;
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen)) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    const int64_t total = a.tiles * a.splits;
+    const unsigned grid = (unsigned)std::min<int64_t>(total, num_sms());
+    kern<<<grid, CF_THREADS, smem, st>>>(a);
+    RC_CHECK_LAUNCH("adc_scan_u8_kernel");
+    return RC_OK;
+}
+
+static int launch_u8(PackScanArgs a, bool sample, cudaStream_t st) {
+    if (a.nq <= 0 || a.npos <= 0) return RC_OK;
+    const U8Cfg c = u8_cfg(a.M);
+    const int docs_per_it = (CF_THREADS / 32) * (32 / c.lpd);
+    a.tiles = (a.nq + c.eb - 1) / c.eb;
+    int64_t pps = (32 * (int64_t)num_sms() + a.tiles - 1) / a.tiles;        // splits wanted
+    pps = (a.npos + pps - 1) / pps;                                          // -> positions per split
+    pps = std::min<int64_t>(pps, (8 << 20) / a.M);
+    pps = std::max<int64_t>(pps, 16384);
+    pps = (pps + docs_per_it - 1) / docs_per_it * docs_per_it;
+    a.pos_per_split = pps;
+    a.splits = (a.npos + pps - 1) / pps;
+    if (sample) RC_CUDA(cudaMemsetAsync(a.item_ctr, 0, 4, st));
+    if (!sample) {
+        // LSU wavefronts per group of (32 / lpd) documents x eb queries: gathers (eb / 4 per warp-wide load),
+        // exchange shuffles, code loads
+        const int ne = a.M / c.lpd;
+        const int shuffles = c.eb == 16 ? (c.lpd == 8 ? 7 : c.lpd == 4 ? 6 : 4) : (c.lpd == 8 ? 4 : 3);
+        const int al = ne % 8 == 0 ? 8 : ne % 4 == 0 ? 4 : ne % 2 == 0 ? 2 : 1;
+        const double per_group = (double)ne * (c.eb / 4) + shuffles + (double)(ne / al);
+        g_scan_wavefronts += (double)a.tiles * ((double)a.npos / (32 / c.lpd)) * per_group;
+        g_scan_kernel = c.eb == 16 ? "adc_scan_u8_kernel<16 queries/entry>" : "adc_scan_u8_kernel<8 queries/entry>";
+    }
+#define RC_U8(MT, EB, LPD, ACC)                                              \
+    case (MT * 100 + LPD * 10 + ACC):                                        \
+        return sample ? launch_u8_inst<MT, EB, LPD, ACC, true>(a, st) : launch_u8_inst<MT, EB, LPD, ACC, false>(a, st)
+    switch (a.M * 100 + c.lpd * 10 + c.acc) {
+        RC_U8(8, 16, 8, 2); RC_U8(16, 16, 8, 2); RC_U8(24, 16, 8, 2); RC_U8(40, 16, 8, 2); RC_U8(80, 8, 8, 2);
+        RC_U8(32, 16, 4, 2); RC_U8(32, 16, 2, 2); RC_U8(32, 16, 8, 2);
+        RC_U8(48, 16, 4, 2); RC_U8(48, 16, 2, 2); RC_U8(48, 16, 4, 3); RC_U8(48, 16, 8, 2);
+        RC_U8(64, 8, 4, 2); RC_U8(64, 8, 8, 2);
+        RC_U8(96, 8, 4, 2); RC_U8(96, 8, 8, 2);
+        default: break;
+    }
+#undef RC_U8
+    set_error("launch_u8: unsupported M=%d lpd=%d acc=%d", a.M, c.lpd, c.acc);
+    return RC_E_UNSUPPORTED;
+}
+
+// threshold of the 8-bit scan from the r-th largest sample sum S_r: T = S_r - ceil(0.501 M + slack) - 1, so that
+// about `target` documents have an exact score above what an excluded document (sum <= T - 1) can reach (the
+// bound adc_rescore_sort_kernel applies)
+__global__ void adc_u8_threshold_kernel(const float* __restrict__ step, const double* __restrict__ sumabs, int M,
+                                        int64_t nq, int* __restrict__ thr_i) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double slack = (double)M * 1.2e-7 * sumabs[q] / (double)step[q] + 1.0;
+    double sh = ceil(0.501 * (double)M + slack) + 1.0;
+    if (!(sh < 65536.0)) sh = 65536.0;        // NaN / degenerate tables: everything passes, the exact re-score decides
+    const int t = thr_i[q] - (int)sh;
+    thr_i[q] = t < 0 ? 0 : t;
 }
 
 // r-th largest 16-bit integer sum of a sample row (2 radix passes); the filter threshold of the packed scan
@@ -999,12 +1413,58 @@ sort_candidates_kernel(const unsigned long long* __restrict__ cand, int cap, con
     if (threadIdx.x == 0) status[q] = 0;
 }
 
-// exact re-scoring of the packed scan's survivors + sort.  One CTA per query: every candidate document is
-// scored in fp32, m ascending, from the query's fp32 table (L2-resident), kept if it reaches the exact
-// threshold, then the survivors are sorted like sort_candidates_kernel does.
-// status: 0 ok, 1 fewer than k_eff exact survivors, 2 the approximate list overflowed, 3 too many survivors
+// exact fp32 scores (m ascending) of the candidates of one query, NC candidates per thread in flight; rows are read
+// as NV 8-byte words (M a multiple of 8, M <= 8 NV)
+template <int NV, int NC, typename Keep>
+__device__ __forceinline__ void rescore_rows(const uint32_t* __restrict__ src, unsigned int n,
+                                             const uint8_t* __restrict__ codes, int M, const float* t, Keep keep) {
+    const int nv = M >> 3;
+    for (unsigned int i = threadIdx.x; i < n; i += NC * SEL_THREADS) {
+        uint32_t doc[NC];
+        uint2 a[NC][NV];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) doc[c] = i + c * SEL_THREADS < n ? src[i + c * SEL_THREADS] : src[i];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const uint2* r = reinterpret_cast<const uint2*>(codes + (int64_t)doc[c] * M);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (v < nv) a[c][v] = __ldg(r + v);
+        }
+        float sc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) sc[c] = 0.0f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            if (v < nv) {
+                const float* tv = t + v * 8 * ADC_K;
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const uint32_t w = bb < 4 ? a[c][v].x : a[c][v].y;
+                        sc[c] += tv[bb * ADC_K + ((w >> (8 * (bb & 3))) & 0xffu)];
+                    }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (i + c * SEL_THREADS < n) keep(sc[c], doc[c]);
+    }
+}
+
+// exact re-scoring of the integer filter's survivors + sort.  One CTA per query: the query's fp32 table is staged
+// in shared memory (when it fits), every candidate document is scored in fp32, m ascending (= a sequential CPU
+// scan, bit for bit), kept if it can belong to the result, and the kept ones are sorted like
+// sort_candidates_kernel does.
+//   thr != NULL : exact fp32 threshold tau known (fp32 sampling) -> keep score >= tau
+//   thr == NULL : only the integer threshold T is known (integer-domain sampling).  A document the scan left out
+//                 has integer sum <= T - 1, hence (quantisation bound, see adc_int_threshold_kernel) exact score
+//                 <= ub = sumlo + step * (T - 1 + 0.501 M + slack): keep what is STRICTLY above ub; the result is
+//                 exact iff at least k documents are kept.
+// status: 0 ok, 1 fewer than k_eff kept, 2 the approximate list overflowed, 3 too many kept for the sort
 __global__ void __launch_bounds__(SEL_THREADS)
-adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict__ codes, int M,
+adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict__ codes, int M, int lut_in_smem,
                         const float* __restrict__ thr, const int* __restrict__ thr_i,
                         const float* __restrict__ qstep, const double* __restrict__ qsumlo,
                         const double* __restrict__ qsumabs, const uint32_t* __restrict__ cand, int cap,
@@ -1020,29 +1480,52 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
         return;
     }
     if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     const float* t = lut + q * (int64_t)M * ADC_K;
-    // thr != NULL : exact fp32 threshold known (fp32 sampling) -> keep score >= tau
-    // thr == NULL : only the integer threshold T is known (integer-domain sampling) -> keep everything and
-    //               verify afterwards that the k-th kept score beats every document the scan left out
+    if (lut_in_smem) {
+        float* ts = reinterpret_cast<float*>(skeys + CAND_CAP);
+        const float4* src4 = reinterpret_cast<const float4*>(t);
+        for (int i = threadIdx.x; i < M * (ADC_K / 4); i += SEL_THREADS) reinterpret_cast<float4*>(ts)[i] = __ldg(src4 + i);
+        t = ts;
+    }
+    __syncthreads();
     const float tau = thr ? thr[q] : -FLT_MAX;
-    const uint32_t* src = cand + q * (int64_t)cap;
-    for (unsigned int i = threadIdx.x; i < c_approx; i += SEL_THREADS) {
-        const uint32_t doc = src[i];
-        const uint8_t* cp = codes + (int64_t)doc * M;
-        float sc = 0.0f;
-        if ((M & 3) == 0) {
-            for (int w = 0; w < M / 4; ++w) {
-                const uint32_t ww = __ldg(reinterpret_cast<const uint32_t*>(cp) + w);
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) sc += __ldg(t + (w * 4 + bb) * ADC_K + ((ww >> (8 * bb)) & 0xffu));
-            }
-        } else {
-            for (int m = 0; m < M; ++m) sc += __ldg(t + m * ADC_K + __ldg(cp + m));
+    double ub = -DBL_MAX;
+    if (!thr) {
+        const double st = (double)qstep[q];
+        const double slack = (double)M * 1.2e-7 * qsumabs[q] / st + 1.0;
+        ub = qsumlo[q] + st * ((double)thr_i[q] - 1.0 + (double)M * 0.501 + slack);
+        if (!(ub == ub)) {                   // NaN bound (non-finite table): exact fallback
+            if (threadIdx.x == 0) { status[q] = 1; exact_cnt[q] = 0; }
+            return;
         }
-        if (sc >= tau) {
+    }
+    const uint32_t* src = cand + q * (int64_t)cap;
+    auto keep = [&](float sc, uint32_t doc) {
+        if (thr ? (sc >= tau) : ((double)sc > ub)) {
             const unsigned int pos = atomicAdd(&s_cnt, 1u);
             if (pos < (unsigned int)CAND_CAP) skeys[pos] = pack_cand(sc, doc);
+        }
+    };
+    if ((M & 7) == 0 && M <= 96 && ((uintptr_t)codes & 7) == 0) {
+        // the usual widths: the whole code row of a candidate (two candidates for M <= 48) is requested before
+        // anything is used -- the loop is bound by the latency of these scattered reads -- then scored m ascending
+        if (M <= 48) rescore_rows<6, 2>(src, c_approx, codes, M, t, keep);
+        else rescore_rows<12, 1>(src, c_approx, codes, M, t, keep);
+    } else {
+        for (unsigned int i = threadIdx.x; i < c_approx; i += SEL_THREADS) {
+            const uint32_t doc = src[i];
+            const uint8_t* cp = codes + (int64_t)doc * M;
+            float sc = 0.0f;
+            if ((M & 3) == 0) {
+                for (int w = 0; w < M / 4; ++w) {
+                    const uint32_t ww = __ldg(reinterpret_cast<const uint32_t*>(cp) + w);
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) sc += t[(w * 4 + bb) * ADC_K + ((ww >> (8 * bb)) & 0xffu)];
+                }
+            } else {
+                for (int m = 0; m < M; ++m) sc += t[m * ADC_K + __ldg(cp + m)];
+            }
+            keep(sc, doc);
         }
     }
     __syncthreads();
@@ -1056,19 +1539,6 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
     while (n < (int)c) n <<= 1;
     for (int i = (int)c + threadIdx.x; i < n; i += SEL_THREADS) skeys[i] = 0ull;
     bitonic_sort_desc(skeys, n);
-    if (!thr) {
-        // a document the scan left out has integer sum <= T - 1, hence (quantisation bound, see
-        // adc_int_threshold_kernel) exact score <= sumlo + step * (T - 1 + 0.501 M + slack): the result is
-        // exact iff the k-th kept score is strictly above that
-        const double st = (double)qstep[q];
-        const double slack = (double)M * 1.2e-7 * qsumabs[q] / st + 1.0;
-        const double ub = qsumlo[q] + st * ((double)thr_i[q] - 1.0 + (double)M * 0.501 + slack);
-        const float sk = key_to_f32((uint32_t)(skeys[k_eff - 1] >> 32));
-        if (!((double)sk > ub)) {
-            if (threadIdx.x == 0) status[q] = 1;
-            return;
-        }
-    }
     for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
         if (i < k_eff) {
             const unsigned long long key = skeys[i];
@@ -1183,12 +1653,12 @@ static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPl
     const size_t o_fl = take((size_t)FB_ROWS * M * ADC_K * 4);
     const size_t o_fs = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 4);
     const size_t o_fi = take((size_t)FB_ROWS * std::max<int64_t>(k, 1) * 8);
-    const size_t o_ql = take((size_t)((qc + 7) / 8 * 8) * M * ADC_K * 2);      // whole tiles of 8 / 4 queries
+    const size_t o_ql = take((size_t)((qc + 15) / 16 * 16) * M * ADC_K * 2);   // whole tiles of 16 / 8 / 4 queries
     const size_t o_qs = take((size_t)qc * 4);
     const size_t o_qo = take((size_t)qc * 8);
     const size_t o_qa = take((size_t)qc * 8);
     const size_t o_ti = take((size_t)qc * 4);
-    const size_t o_c32 = take((size_t)qc * CAND_CAP * 4);
+    const size_t o_c32 = take((size_t)qc * CAND_CAP32 * 4);
     const size_t o_ec = take((size_t)qc * 4);
     const size_t o_ic = take(16);
     if (w) {
@@ -1232,7 +1702,7 @@ static int sort_smem_attr() {
     static unsigned long long attr_seen = 0ull;
     if (first_use_on_device(attr_seen)) {
         RC_CUDA(cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
-        RC_CUDA(cudaFuncSetAttribute(adc_rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
+        RC_CUDA(cudaFuncSetAttribute(adc_rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         RC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CAND_CAP * 8));
     }
     return RC_OK;
@@ -1341,33 +1811,41 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         RC_CUDA(cudaEventCreate(&ev1));
     }
 
-    // balanced chunks (a multiple of 8 queries: whole CTA tiles of the packed scan)
+    // balanced chunks (a multiple of 16 queries: whole CTA tiles of the packed scans)
     const int64_t n_chunks = (nq + Q_CHUNK - 1) / Q_CHUNK;
-    const int64_t chunk = std::min<int64_t>(Q_CHUNK, ((nq + n_chunks - 1) / n_chunks + 7) / 8 * 8);
+    const int64_t chunk = std::min<int64_t>(Q_CHUNK, ((nq + n_chunks - 1) / n_chunks + 15) / 16 * 16);
+    const bool codes_aligned = ((uintptr_t)codes & 7) == 0;     // the 8-bit scan loads a lane's code bytes as one vector
     for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
         const int64_t qc = std::min<int64_t>(chunk, nq - c0);
-        const int qmax = 65535 / M;
         const bool int_sampling = !p.dense_all && cf_capable(M) && !adc_force_gather();
+        const bool fields8 = int_sampling && u8_enabled(M) && codes_aligned;
+        const U8Cfg u8 = u8_cfg(M);
+        const int qmax = fields8 ? 255 / u8.acc : 65535 / M;
+        const int cand_cap = fields8 ? CAND_CAP32 : CAND_CAP;
         if (int_sampling) {
             // fp32 tables + integer tables in the scan's shared-memory layout, one kernel
-            const int qp = cf_qp(M);
+            const int qp = fields8 ? u8.eb : cf_qp(M);
             const unsigned tiles = (unsigned)((qc + qp - 1) / qp);
-            const size_t sm = ((size_t)qp * M * ds + (size_t)qp * M + 8 * qp * 2 + qp) * 4;
+            const size_t sm = ((size_t)qp * M * ds + (size_t)M * 8 * qp * 2 + 2 * (size_t)qp * M + qp) * 4;
             static unsigned long long attr_seen = 0ull;
             if (first_use_on_device(attr_seen)) {
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             }
             if (sm > 160 * 1024) {
                 set_error("rc_adc_search: query dimension %d too large for the table builder", M * ds);
                 return RC_E_UNSUPPORTED;
             }
-            if (qp == 8)
-                adc_lut_pack_kernel<8><<<tiles, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, w.lut,
-                                                               w.qlut, w.qstep, w.qsumlo, w.qsumabs);
-            else
-                adc_lut_pack_kernel<4><<<tiles, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, w.lut,
-                                                               w.qlut, w.qstep, w.qsumlo, w.qsumabs);
+#define RC_LUT_PACK(QP, U8)                                                                                          \
+    adc_lut_pack_kernel<QP, U8><<<tiles, LP_THREADS, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, u8.lpd, \
+                                                       w.lut, w.qlut, w.qstep, w.qsumlo, w.qsumabs)
+            if (fields8 && qp == 16) RC_LUT_PACK(16, true);
+            else if (fields8) RC_LUT_PACK(8, true);
+            else if (qp == 8) RC_LUT_PACK(8, false);
+            else RC_LUT_PACK(4, false);
+#undef RC_LUT_PACK
             RC_CHECK_LAUNCH("adc_lut_pack_kernel");
         } else {
             rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
@@ -1401,12 +1879,16 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
             a.blk = SAMPLE_BLK; a.stride = p.stride; a.out16 = reinterpret_cast<uint16_t*>(w.dense);
             a.ld16 = p.n_sample;
             a.item_ctr = w.item_ctr;
-            rc = launch_cf(a, true, st);
+            rc = fields8 ? launch_u8(a, true, st) : launch_cf(a, true, st);
             if (rc) return rc;
             radix_select_u16_kernel<<<(unsigned)qc, SEL_THREADS, 0, st>>>(reinterpret_cast<uint16_t*>(w.dense),
                                                                            p.n_sample, p.n_sample, p.rank_sample,
                                                                            w.thr_i);
             RC_CHECK_LAUNCH("radix_select_u16_kernel");
+            if (fields8) {
+                adc_u8_threshold_kernel<<<(unsigned)((qc + 255) / 256), 256, 0, st>>>(w.qstep, w.qsumabs, M, qc, w.thr_i);
+                RC_CHECK_LAUNCH("adc_u8_threshold_kernel");
+            }
         } else {
             ScanArgs a{};
             a.lut = w.lut; a.codes = codes; a.nq = qc; a.npos = p.n_sample; a.blk = SAMPLE_BLK; a.stride = p.stride;
@@ -1425,18 +1907,20 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         {
             PackScanArgs a{};
             a.qlut = w.qlut; a.codes = codes; a.thr_i = w.thr_i; a.nq = qc; a.npos = N; a.M = M;
-            a.cnt = w.cnt; a.cand = w.cand32; a.cap = CAND_CAP;
+            a.cnt = w.cnt; a.cand = w.cand32; a.cap = cand_cap;
             a.item_ctr = w.item_ctr + 1;
             if (int_sampling) RC_CUDA(cudaMemsetAsync(a.item_ctr, 0, 4, st));   // (outside the timed region)
             if (ev0) RC_CUDA(cudaEventRecord(ev0, st));
-            rc = int_sampling ? launch_cf(a, false, st) : launch_packed(a, st);
+            rc = fields8 ? launch_u8(a, false, st) : int_sampling ? launch_cf(a, false, st) : launch_packed(a, st);
             if (rc) return rc;
             if (ev1) RC_CUDA(cudaEventRecord(ev1, st));
         }
         // 3. exact re-score of the survivors + per-query sort
-        adc_rescore_sort_kernel<<<(unsigned)qc, SEL_THREADS, CAND_CAP * 8, st>>>(
-            w.lut, codes, M, int_sampling ? nullptr : w.thr, w.thr_i, w.qstep, w.qsumlo, w.qsumabs, w.cand32, CAND_CAP,
-            w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status, w.exact_cnt);
+        const size_t lut_bytes = (size_t)M * ADC_K * 4;
+        const int lut_in_smem = (size_t)CAND_CAP * 8 + lut_bytes <= 200 * 1024 ? 1 : 0;
+        adc_rescore_sort_kernel<<<(unsigned)qc, SEL_THREADS, (size_t)CAND_CAP * 8 + (lut_in_smem ? lut_bytes : 0), st>>>(
+            w.lut, codes, M, lut_in_smem, int_sampling ? nullptr : w.thr, w.thr_i, w.qstep, w.qsumlo, w.qsumabs, w.cand32,
+            cand_cap, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status, w.exact_cnt);
         RC_CHECK_LAUNCH("adc_rescore_sort_kernel");
         // 4. queries whose list under/overflowed take the exact dense path
         status_h.resize(qc);

@@ -32,7 +32,11 @@ if "assign" in what:
               f"{M * B * 256 * 4 / per_pass / 1e6:.0f} GB/s", flush=True)
 if "adc" in what:
     N = int(os.environ.get("QB_N", 8841823))
-    for (M, nq, k) in [(48, 1200, 1000), (32, 1200, 1000), (64, 1200, 1000), (96, 1200, 1000), (48, 128, 200)]:
+    cases = [(48, 1200, 1000), (32, 1200, 1000), (64, 1200, 1000), (96, 1200, 1000), (48, 128, 200)]
+    if os.environ.get("QB_M"):
+        cases = [(int(m), 1200, 1000) for m in os.environ["QB_M"].split(",")]
+    _lib.load().rc_adc_enable_timing(1)
+    for (M, nq, k) in cases:
         ds = 768 // M
         codes = torch.randint(0, 256, (N, M), generator=gen, device="cuda", dtype=torch.uint8)
         c = torch.randn((M, 256, ds), generator=gen, device="cuda")
@@ -40,7 +44,7 @@ if "adc" in what:
         idx = GpuIndexPQ(codes, c)
         t = timeit(lambda: idx.search_tensor(q, k), n=2)
         print(f"adc N={N} M={M} nq={nq} k={k}: {t[0]:.1f} ms -> {nq / t[0] * 1e3:.0f} QPS, "
-              f"{nq * N * M / t[0] / 1e6:.0f} G lookups/s, alg {nq * N * M / t[0] / 1e6:.0f} GB/s, stats {idx.last_stats}",
-              flush=True)
+              f"{nq * N * M / t[0] / 1e6:.0f} G lookups/s, scan {_lib.load().rc_adc_last_scan_ms():.2f} ms, "
+              f"stats {idx.last_stats}", flush=True)
         del codes, idx
 print("launches", _lib.launch_count())
