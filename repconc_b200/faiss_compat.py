@@ -303,18 +303,25 @@ class GpuIndexPQ:
         if n == 0:
             return out_s, out_i
         with torch.cuda.device(self.device):
-            ids_dev = self._resident_ids(corpus_ids) if (corpus_ids is not None and copy_back) else None
-            if corpus_ids is not None and copy_back and ids_dev is None:
-                raise TypeError("search_batches: corpus_ids must be an int64 array")
             compute = torch.cuda.current_stream()
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._up_stream = torch.cuda.Stream(device=self.device)
             # rc_adc_search returns only when the scan has finished (it reads the survivor counters back), so the
             # copy-back of batch i is drained by a helper thread while the caller's thread sits in the scan of
-            # batch i+1 (ctypes and numpy's block copies both release the GIL).
+            # batch i+1 (ctypes and numpy's block copies both release the GIL).  A second helper validates the
+            # cached device copy of the id table and stages / uploads the queries of the later batches while the
+            # first batch is scanned.
             if getattr(self, "_drain_pool", None) is None:
                 from concurrent.futures import ThreadPoolExecutor
                 self._drain_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="repconc-drain")
+                self._stage_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="repconc-stage")
+            dev_index = self.device.index
+
+            def resident_ids():
+                with torch.cuda.device(dev_index):
+                    return self._resident_ids(corpus_ids)
+
             busy = [None, None]     # per staging slot: future of the drain that still reads it
             lo = 0
 
@@ -330,26 +337,48 @@ class GpuIndexPQ:
                 if trace is not None:
                     trace.append((label, _time.perf_counter()))
 
-            # all queries go to the device up front (one staging pass + one DMA, in groups of <= 256 MB): the
-            # caller's thread then does no large host copy while the helper thread drains results
+            # queries go to the device in groups: the first batch alone (so that the scan starts at once), then the
+            # rest in groups of <= 256 MB, each staged into pinned memory and uploaded on its own stream by the
+            # staging helper while earlier batches are scanned.  Two pinned / device buffers alternate.
             group_rows = max(1, (256 << 20) // (self.d * 4))
-            xd_group, g_lo, g_hi = None, 0, 0
-
-            def load_group(start_batch, row0):
-                rows, bj = 0, start_batch
-                while bj < len(batches) and (rows == 0 or rows + sizes[bj] <= group_rows):
+            groups = []                                   # (first batch, end batch, first row, end row)
+            bj, row = 0, 0
+            while bj < len(batches):
+                rows, b0 = 0, bj
+                while bj < len(batches) and (rows == 0 or (b0 > 0 and rows + sizes[bj] <= group_rows)):
                     rows += sizes[bj]
                     bj += 1
-                hx = self._pinned("xg", (rows, self.d), torch.float32)
-                r = 0
-                for b in batches[start_batch:bj]:
-                    b = np.ascontiguousarray(b, dtype=np.float32)
-                    if b.ndim != 2 or b.shape[1] != self.d:
-                        raise ValueError(f"query_embeds: expected (nq, {self.d}), got {b.shape}")
-                    hx[r:r + len(b)].copy_(torch.from_numpy(b))
-                    r += len(b)
-                compute.synchronize()                     # the pinned buffer is free (previous group consumed)
-                return hx.to(self.device, non_blocking=True), row0, row0 + rows
+                groups.append((b0, bj, row, row + rows))
+                row += rows
+            free_ev = [None, None]                        # per group slot: event after its last search was enqueued
+
+            def load_group(gi):
+                b0, b1, r0, r1 = groups[gi]
+                with torch.cuda.device(dev_index):
+                    hx = self._pinned(f"xg{gi & 1}", (r1 - r0, self.d), torch.float32)
+                    r = 0
+                    for b in batches[b0:b1]:
+                        b = np.ascontiguousarray(b, dtype=np.float32)
+                        if b.ndim != 2 or b.shape[1] != self.d:
+                            raise ValueError(f"query_embeds: expected (nq, {self.d}), got {b.shape}")
+                        hx[r:r + len(b)].copy_(torch.from_numpy(b))
+                        r += len(b)
+                    with torch.cuda.stream(self._up_stream):
+                        xd = hx.to(self.device, non_blocking=True)
+                        up = torch.cuda.Event()
+                        up.record(self._up_stream)
+                    return xd, up
+
+            def submit_group(gi):
+                # the pinned buffer of this slot was last read by the upload of group gi - 2, which the caller waited
+                # for (future + event) before searching that group: free by construction
+                return self._stage_pool.submit(load_group, gi) if gi < len(groups) else None
+
+            first = submit_group(0)
+            ids_future = self._stage_pool.submit(resident_ids) if (corpus_ids is not None and copy_back) else None
+            group_future = [first, submit_group(1)]
+            cur_group, xd_group, g_lo, g_hi = -1, None, 0, 0
+            ids_dev = None
 
             for bi, xb in enumerate(batches):
                 nb = sizes[bi]
@@ -358,7 +387,15 @@ class GpuIndexPQ:
                 slot = bi & 1
                 mark("begin")
                 if lo >= g_hi:
-                    xd_group, g_lo, g_hi = load_group(bi, lo)
+                    cur_group += 1
+                    xd_group, up = group_future[cur_group & 1].result()
+                    compute.wait_event(up)
+                    xd_group.record_stream(compute)
+                    _, _, g_lo, g_hi = groups[cur_group]
+                    # the other slot belonged to the previous group, whose searches have all returned (rc_adc_search
+                    # synchronises): its pinned buffer can be refilled
+                    if cur_group >= 1:
+                        group_future[(cur_group + 1) & 1] = submit_group(cur_group + 1)
                 mark("staged")
                 xd = xd_group[lo - g_lo: lo - g_lo + nb]
                 mark("h2d")
@@ -367,7 +404,11 @@ class GpuIndexPQ:
                 if not copy_back:
                     lo += nb
                     continue
-                if ids_dev is not None:
+                if ids_future is not None:
+                    if ids_dev is None:
+                        ids_dev = ids_future.result()
+                        if ids_dev is None:
+                            raise TypeError("search_batches: corpus_ids must be an int64 array")
                     mapped = torch.empty_like(i)
                     _lib.check(_lib.load().rc_map_ids(i.data_ptr(), ids_dev.data_ptr(), ids_dev.numel(), i.numel(),
                                                       mapped.data_ptr(), ops._stream()), "rc_map_ids")
