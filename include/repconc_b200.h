@@ -126,12 +126,13 @@ int rc_sinkhorn_expand(const float* table, int64_t B, int64_t B_global, int M, i
 int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M, int K, double eps, int iters,
                       int dense, void* state, int64_t* codes_mb, uint8_t* codes_u8, int32_t* flags,
                       void* stream);
-/* W-rank solve with the per-iteration exchange of the row sums FUSED into the persistent kernel: the
+/* W-rank solve with the per-iteration exchange of the row sums FUSED into the row-sum kernel: the
  * `dist.all_reduce(sum_of_rows)` of modeling_repconc.py:156-157 (M x K fp64 every iteration) happens
- * inside the pass that produces the sums -- the last CTA to finish sub-vector m publishes its 256 sums
- * in a symmetric buffer, raises a flag on every peer (system-scope release store over NVLink), waits for
- * the W flags, sums the W vectors in rank order straight from peer memory (bitwise identical on every
- * rank) and updates the row scaling of m, while other sub-vectors are still being scanned.
+ * inside the kernel that reduces the sums -- block m PUSHES its 256 sums into every peer's symmetric
+ * buffer as 16-byte words {low half, seq, high half, seq} (every 8-byte half carries the sequence number
+ * of the exchange, so no fence and no separate flag are needed), polls its own buffer for the peers'
+ * words, sums the W vectors in rank order (bitwise identical on every rank) and updates the row scaling
+ * of m.  One NVLink store latency per exchange (measured 1-3 us on 2 B200s).
  *   peer_buffers_host  HOST array of W device pointers: rank p's symmetric buffer as mapped into THIS
  *                      process, rc_sinkhorn_peer_buffer_bytes(M, K) bytes each, zero-initialised ONCE
  *                      (e.g. torch.distributed._symmetric_memory); reused by later calls

@@ -1414,42 +1414,84 @@ __device__ __forceinline__ double ld_relaxed_sys_f64x(const double* p) {
     asm("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-__host__ __device__ constexpr size_t sk_peer_header_bytes(int M) { return (size_t)2 * M * PEERX_MAX_W * 4; }
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+// symmetric buffer of the fused exchange: [parity 2][sub-vector M][source rank 16][k 256] 16-byte words
+__host__ __device__ constexpr size_t sk_peer_buffer_bytes(int M) { return (size_t)2 * M * PEERX_MAX_W * SP_K * 16; }
 
 // reduce + (exchange) + update of sub-vector m by one block; u = index of the update (0 = after BEGIN)
 template <int W_T>
 __device__ __forceinline__ bool sk_reduce_update_m(int m, unsigned int u, const SkPart& part, const SkState& st, int M,
                                                    int32_t* __restrict__ flags, const SkPeer& peer, int* s_off,
                                                    double* s_red, int* s_flag) {
+#ifdef RC_XCHG_PROFILE
+    unsigned long long xt[6];
+    auto xlap = [&](int i) { if (m == 0 && threadIdx.x == 0) xt[i] = global_timer_ns(); };
+    xlap(0);
+#else
+    auto xlap = [&](int) {};
+#endif
     sk_reduce_m(m, st.partial, part, SP_K, st.P, s_off);
+    xlap(1);
     if (W_T != 1) {
+        // Exchange without fences or separate flags (the idea of NCCL's LL protocol): a rank PUSHES its 256 sums into
+        // every peer's buffer as 16-byte words {low half, seq, high half, seq} -- each 8-byte half carries the sequence
+        // number of this exchange and 8-byte stores are single-copy atomic, so a reader that sees `seq` in a half sees
+        // that half's data -- and every thread polls ITS element of each peer in local memory.  One NVLink store
+        // latency per exchange; the publish + system fence + flag round trip + remote reads it replaces cost 14 us.
+        // Slot reuse: parity of seq; a rank sends exchange s+1 only after it finished reading exchange s, and its
+        // peers cannot send s+2 before they received its s+1.
         const int W = W_T > 0 ? W_T : peer.W;
         const uint32_t seq = peer.seq_base + u + 1u;
         const size_t par = seq & 1u;
-        const size_t hdr = sk_peer_header_bytes(M);
-        const size_t voff = (par * M + m) * SP_K;
-        const size_t fidx = (par * M + m) * PEERX_MAX_W;
-        // 1. publish this rank's 256 sums (each thread re-reads the value it stored itself)
-        reinterpret_cast<double*>(peer.base[peer.rank] + hdr)[voff + threadIdx.x] =
-            __ldcg(st.P + (int64_t)m * SP_K + threadIdx.x);
-        __threadfence_system();
+        const double mine = __ldcg(st.P + (int64_t)m * SP_K + threadIdx.x);   // (each thread re-reads its own store)
+        const uint32_t lo = (uint32_t)__double2loint(mine), hi = (uint32_t)__double2hiint(mine);
+        const size_t slot_m = (par * M + m) * PEERX_MAX_W;
         if (threadIdx.x == 0) *s_flag = 0;
+#pragma unroll
+        for (int p = 0; p < PEERX_MAX_W; ++p)
+            if (p < W && p != peer.rank)
+                st_volatile_v4(reinterpret_cast<uint4*>(peer.base[p]) + (slot_m + peer.rank) * SP_K + threadIdx.x,
+                               make_uint4(lo, seq, hi, seq));
         __syncthreads();
-        // 2. signal every peer, 3. wait for every peer
-        if ((int)threadIdx.x < W) {
-            st_release_sys_u32(reinterpret_cast<uint32_t*>(peer.base[threadIdx.x]) + fidx + peer.rank, seq);
-            const uint32_t* my = reinterpret_cast<const uint32_t*>(peer.base[peer.rank]) + fidx + threadIdx.x;
-            const unsigned long long t0 = global_timer_ns();
-            unsigned int spins = 0;
-            while ((int32_t)(ld_acquire_sys_u32(my) - seq) < 0) {        // sequence numbers only grow (wrap-safe)
-                if ((++spins & 255u) == 0u &&
-                    (global_timer_ns() - t0 > peer.timeout_ns || *reinterpret_cast<volatile unsigned int*>(st.abort_w))) {
-                    *s_flag = 1;
-                    break;
+        xlap(2);
+        double v[PEERX_MAX_W];
+        const uint4* inbox = reinterpret_cast<const uint4*>(peer.base[peer.rank]) + slot_m * SP_K + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        uint32_t pending = 0u;
+#pragma unroll
+        for (int p = 0; p < PEERX_MAX_W; ++p)
+            if (p < W && p != peer.rank) pending |= 1u << p;
+        while (pending) {
+#pragma unroll
+            for (int p = 0; p < PEERX_MAX_W; ++p) {
+                if ((pending >> p) & 1u) {
+                    const uint4 w = ld_volatile_v4(inbox + (size_t)p * SP_K);
+                    if (w.y == seq && w.w == seq) {
+                        v[p] = __hiloint2double((int)w.z, (int)w.x);
+                        pending &= ~(1u << p);
+                    }
                 }
+            }
+            if (pending && (++spins & 255u) == 0u &&
+                (global_timer_ns() - t0 > peer.timeout_ns || *reinterpret_cast<volatile unsigned int*>(st.abort_w))) {
+                *s_flag = 1;
+                break;
             }
         }
         __syncthreads();
+        xlap(3);
         if (*s_flag) {
             if (threadIdx.x == 0) {
                 atomicOr(flags, RC_FLAG_PEER_TIMEOUT);
@@ -1457,19 +1499,23 @@ __device__ __forceinline__ bool sk_reduce_update_m(int m, unsigned int u, const 
             }
             return false;
         }
-        // 4. sum in rank order straight from peer memory: every rank holds the bitwise identical result
-        double v[PEERX_MAX_W];
-#pragma unroll
-        for (int p = 0; p < PEERX_MAX_W; ++p)
-            if (p < W) v[p] = ld_relaxed_sys_f64x(reinterpret_cast<const double*>(peer.base[p] + hdr) + voff + threadIdx.x);
+        // sum in rank order: every rank holds the bitwise identical result
         double sum = 0.0;
 #pragma unroll
         for (int p = 0; p < PEERX_MAX_W; ++p)
-            if (p < W) sum += v[p];
+            if (p < W) sum += p == peer.rank ? mine : v[p];
         __stcg(st.P + (int64_t)m * SP_K + threadIdx.x, sum);
     }
     __syncthreads();
+    xlap(4);
     sk_update_m(m, st, SP_K, u > 0 ? 1 : 0, 1, m >= st.m_half1 ? 1 : 0, u, flags, s_red);
+#ifdef RC_XCHG_PROFILE
+    xlap(5);
+    if (m == 0 && threadIdx.x == 0 && W_T != 1) {
+        for (int i = 0; i < 5; ++i) atomicAdd(st.cta_ns + i, xt[i + 1] - xt[i]);
+        atomicAdd(st.cta_ns + 5, 1ull);
+    }
+#endif
     return true;
 }
 
@@ -1981,6 +2027,9 @@ RC_API int rc_dist_table(const float* x, int64_t ldx, const float* centroids, in
 
 static int sk_reset(const SkState& s, int64_t B, int M, int K, cudaStream_t st) {
     const size_t n = (size_t)M * K * 8;
+#ifdef RC_XCHG_PROFILE
+    RC_CUDA(cudaMemsetAsync(s.cta_ns, 0, 64, st));
+#endif
     if (K == SP_K)   // pair directory: entries of rows past B stay empty
         RC_CUDA(cudaMemsetAsync(s.csr, 0, (size_t)M * ((B + SK_TILE - 1) / SK_TILE) * SK_WARPS * sizeof(uint2), st));
     RC_CUDA(cudaMemsetAsync(s.lu, 0, n, st));              // +0.0
@@ -2098,7 +2147,8 @@ RC_API int rc_sinkhorn_solve(float* table, const float* minmax, int64_t B, int M
 
 RC_API size_t rc_sinkhorn_peer_buffer_bytes(int M, int K) {
     if (M < 1 || K < 1) return 0;
-    return sk_peer_header_bytes(M) + (size_t)2 * M * K * 8;
+    (void)K;
+    return sk_peer_buffer_bytes(M);
 }
 
 RC_API int rc_sinkhorn_solve_peer(float* table, const float* minmax, int64_t B, int64_t B_global, int M, int K,
