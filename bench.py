@@ -8,7 +8,9 @@ Prints ONE JSON line (rank 0).
 
 Primary metric (BASELINE.json configs[1]): PQ asymmetric-distance top-1000 search, 8,841,823 synthetic documents,
 768-d, M=48, K=256; a "step" is one `search_batch` of 1200 queries (evaluate_repconc.py:38) against the whole
-corpus.  N > 1: the same corpus sharded N ways ("strong" at every N, N = 1 included).
+corpus.  N > 1: the same corpus REPLICATED on every GPU with the queries split N ways -- the reference's own multi-GPU
+mode (index_cpu_to_all_gpus, evaluate_repconc.py:130-134); "strong" at every N, N = 1 included.  The corpus-sharded
+search of the same corpus is the secondary record `adc_sharded`.
   value         queries/s with queries and corpus resident in HBM (CUDA events, max over ranks)
   e2e           the same through the reference-facing `batch_search` with HOST numpy queries / results
   roofline      the filtered-scan kernel against the limit that binds it (shared-memory wavefronts per clock per SM)
@@ -291,7 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
-    ap.add_argument("--only", default="adc,assign,adc_c4,assign_c5",
+    ap.add_argument("--only", default="adc,adc_sharded,assign,adc_c4,assign_c5",
                     help="comma-separated workloads to run (the primary `adc` always runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -346,8 +348,10 @@ def main():
             clk_started[0] = True
 
     # ------------------------------------------------------------------ ADC workloads
-    def run_adc(M, n_docs, lo, hi, seed, tag):
-        """One ADC workload: documents [lo, hi) of an n_docs corpus on this rank, all queries on every rank."""
+    def run_adc(M, n_docs, lo, hi, seed, tag, replicated=False):
+        """One ADC workload: documents [lo, hi) of an n_docs corpus on this rank.  Corpus-sharded: all queries on
+        every rank, per-shard lists exchanged and merged.  `replicated` (lo, hi = whole corpus on every rank): the
+        queries are split over the ranks, the reference's own multi-GPU mode (evaluate_repconc.py:130-134)."""
         n_q = (W + Ksteps) * SEARCH_BATCH
         codes, cent, q_all, rel = make_eval_set(torch, ops, dev, M, n_docs, lo, hi, n_q, seed)
         index = GpuIndexPQ(codes, cent, id_offset=lo)
@@ -355,7 +359,9 @@ def main():
         q_host = q_dev.cpu().numpy()
         rel = rel.reshape(W + Ksteps, SEARCH_BATCH)
         corpus_ids = np.arange(n_docs, dtype=np.int64)
-        sharded = E.ShardedSearcher(index) if world > 1 else None
+        sharded = None
+        if world > 1:
+            sharded = E.ReplicatedSearcher(index) if replicated else E.ShardedSearcher(index)
 
         def step(i):
             if world > 1:
@@ -378,13 +384,13 @@ def main():
             scan_ms += lib.rc_adc_last_scan_ms()
             scan_launches += lib.rc_adc_last_scan_launches()
             wavefronts += lib.rc_adc_last_scan_wavefronts()
-            fallbacks += index.last_stats["dense"]
+            fallbacks += index.last_stats["dense"] if index.last_stats else 0
         e1.record()
         barrier()
         launches = _lib.launch_count() - l0
         ms = max_over_ranks(e0.elapsed_time(e1))
         qps = Ksteps * SEARCH_BATCH / (ms / 1e3)
-        stats = dict(index.last_stats, fallback_queries_in_timed_region=fallbacks)
+        stats = dict(index.last_stats or {}, fallback_queries_in_timed_region=fallbacks)
         # MRR@10 of the timed queries (N > 1: the merged result is complete on rank 0)
         mrr = mrr_at_10(torch.cat(ids_dev).cpu().numpy(), rel[W:].reshape(-1))
         # e2e: host numpy queries -> batch_search -> host numpy results.  ONE batch_search call over the K steps'
@@ -408,7 +414,8 @@ def main():
         # roofline of the filtered scan (this rank's shard)
         n_shard = hi - lo
         alg_per_query = n_shard * M + 4 * M * K + 12 * TOPK
-        alg_per_launch = alg_per_query * (Ksteps * SEARCH_BATCH) / max(scan_launches, 1)
+        q_per_rank = SEARCH_BATCH / world if (replicated and world > 1) else SEARCH_BATCH
+        alg_per_launch = alg_per_query * (Ksteps * q_per_rank) / max(scan_launches, 1)
         scan_avg_s = scan_ms / 1e3 / max(scan_launches, 1)
         hbm_gbs = alg_per_launch / scan_avg_s / 1e9 if scan_avg_s > 0 else 0.0
         kname = lib.rc_adc_last_scan_kernel().decode()
@@ -458,8 +465,13 @@ def main():
                         "duration / measured HBM peak; it exceeds 1 because 8-16 queries share every code byte a "
                         "CTA reads and a split's codes stay L2-resident (see `traffic` for the DRAM bytes)"}
 
-    lo, hi = E.shard_bounds(C2_DOCS, rank, world)
-    adc = run_adc(C2_M, C2_DOCS, lo, hi, seed=1234, tag="adc")
+    # primary metric at N > 1: index replicas + query split (the corpus fits every GPU; the reference's multi-GPU
+    # mode); the corpus-sharded search of the same corpus is reported beside it, and configs[3] below is sharded
+    adc = run_adc(C2_M, C2_DOCS, 0, C2_DOCS, seed=1234, tag="adc", replicated=True)
+    adc_sharded = None
+    if world > 1 and "adc_sharded" in only:
+        lo, hi = E.shard_bounds(C2_DOCS, rank, world)
+        adc_sharded = run_adc(C2_M, C2_DOCS, lo, hi, seed=1234, tag="adc_sharded")
     adc_c4 = None
     if "adc_c4" in only:
         n4 = C4_DOCS_PER_GPU * world
@@ -617,7 +629,9 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ADC_WORKLOAD},
             "details": {"docs_per_gpu": adc["n_shard"], "queries_per_step": SEARCH_BATCH, "topk": TOPK,
-                        "parallelism": f"corpus-sharded x{world}" if world > 1 else "single GPU",
+                        "parallelism": (f"index replicated on {world} GPUs, queries split (the reference's "
+                                        "index_cpu_to_all_gpus mode, evaluate_repconc.py:130-134); corpus-sharded "
+                                        "search of the same corpus in `adc_sharded`") if world > 1 else "single GPU",
                         "corpus": "SURVEY 8(d): N(0,I) documents coded by rc_nn_assign, queries = document + 0.5 noise",
                         "l2_policy": "inputs larger than L2 (corpus 424 MB vs 126 MB L2); fresh queries every step"},
             "e2e": {"value": adc["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": SEARCH_BATCH * D * 4,
@@ -625,6 +639,9 @@ def main():
             "gpu_launches": adc["launches"], "roofline": adc_roofline(adc, clocks["sm_mhz"]),
             "cpu_baseline": adc["cpu"], "clocks": clocks, "search_stats": adc["stats"], "mrr_at_10": adc["mrr"],
             "assign": assign, "assign_c5": assign_c5,
+            "adc_sharded": adc_record(adc_sharded, ADC_WORKLOAD + f", corpus sharded over {world} GPUs (all queries "
+                                      "on every rank, all_to_all + owner merge)", "strong", C2_DOCS)
+            if adc_sharded else None,
             "adc_c4": adc_record(adc_c4, "corpus-sharded ADC top-1000, 8,000,000 docs per GPU x 768-d, M=32 K=256 "
                                          "(BASELINE configs[3]: 64 M docs on 8 GPUs)", "weak",
                                  C4_DOCS_PER_GPU * world) if adc_c4 else None,

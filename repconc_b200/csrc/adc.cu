@@ -37,7 +37,9 @@ constexpr int ADC_K = 256;
 constexpr int SCAN_THREADS = 512;
 constexpr int SEL_THREADS = 1024;
 constexpr int CAND_CAP = 8192;        // candidate list capacity per query == max sortable k
-constexpr int CAND_CAP32 = 32768;    // capacity of the integer filter's list (document positions, re-scored exactly)
+constexpr int CAND_CAP32 = 65536;    // capacity of the integer filter's list (document positions, re-scored exactly)
+// list capacity actually used: the 8-bit fields of wide codes keep more candidates (M = 96: ~26 k per query measured)
+static int cand_cap32(int M) { return M >= 80 ? CAND_CAP32 : CAND_CAP32 / 2; }
 constexpr int Q_CHUNK = 2048;         // max queries processed per pass of the host loop
 constexpr int FB_ROWS = 4;            // exact-fallback queries per dense scan
 constexpr int64_t DENSE_N_MAX = 262144;  // corpora up to this size take the dense path
@@ -1413,17 +1415,21 @@ sort_candidates_kernel(const unsigned long long* __restrict__ cand, int cap, con
     if (threadIdx.x == 0) status[q] = 0;
 }
 
+constexpr int RS_THREADS = 1024;    // re-score + select + sort: one CTA per query
+constexpr int RS_SEL_MAX = 2048;    // largest k the selection buffer holds (larger k: the filtered path is not used)
+// auxiliary shared memory behind the keys: the fp32 table while re-scoring, then selection buffer + histograms
+constexpr size_t RS_AUX_BYTES = (size_t)RS_SEL_MAX * 8 + (RS_THREADS / 32) * 256 * 4 + 256 * 4;
 // exact fp32 scores (m ascending) of the candidates of one query, NC candidates per thread in flight; rows are read
 // as NV 8-byte words (M a multiple of 8, M <= 8 NV)
 template <int NV, int NC, typename Keep>
 __device__ __forceinline__ void rescore_rows(const uint32_t* __restrict__ src, unsigned int n,
                                              const uint8_t* __restrict__ codes, int M, const float* t, Keep keep) {
     const int nv = M >> 3;
-    for (unsigned int i = threadIdx.x; i < n; i += NC * SEL_THREADS) {
+    for (unsigned int i = threadIdx.x; i < n; i += NC * RS_THREADS) {
         uint32_t doc[NC];
         uint2 a[NC][NV];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) doc[c] = i + c * SEL_THREADS < n ? src[i + c * SEL_THREADS] : src[i];
+        for (int c = 0; c < NC; ++c) doc[c] = i + c * RS_THREADS < n ? src[i + c * RS_THREADS] : src[i];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const uint2* r = reinterpret_cast<const uint2*>(codes + (int64_t)doc[c] * M);
@@ -1449,8 +1455,109 @@ __device__ __forceinline__ void rescore_rows(const uint32_t* __restrict__ src, u
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c)
-            if (i + c * SEL_THREADS < n) keep(sc[c], doc[c]);
+            if (i + c * RS_THREADS < n) keep(sc[c], doc[c]);
     }
+}
+
+// The k largest of n distinct 64-bit keys in shared memory -> aux[0 .. k) (unordered); returns that buffer.
+// Radix select from the highest bit in which the keys differ, 8 bits per pass, per-warp histograms (keys that share
+// their leading bits would serialise on one counter), the bucket search by warp 0.  Ends as soon as a bucket holds
+// exactly the number of keys still needed.  All threads of the block call it; ends with a block barrier.
+__device__ __forceinline__ unsigned long long* rs_select_topk(const unsigned long long* keys, int n, int k,
+                                                              unsigned char* aux) {
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(aux);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(aux + (size_t)RS_SEL_MAX * 8);      // [warps][256]
+    unsigned int* tot = hist + (RS_THREADS / 32) * 256;                                       // [256]
+    __shared__ unsigned long long s_min, s_max, s_prefix, s_mask;
+    __shared__ unsigned int s_need, s_done, s_out;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_min = ~0ull; s_max = 0ull; s_out = 0u; }
+    __syncthreads();
+    {
+        unsigned long long lo = ~0ull, hi = 0ull;
+        for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+            const unsigned long long v = keys[i];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = a < lo ? a : lo;
+            hi = b > hi ? b : hi;
+        }
+        if (lane == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+    }
+    __syncthreads();
+    const unsigned long long diff = s_min ^ s_max;          // != 0: the keys are distinct and n > k >= 1
+    int low = 64 - __clzll((long long)diff);                // bits [low, 64) are common to all keys
+    if (threadIdx.x == 0) {
+        s_mask = low >= 64 ? 0ull : ~((1ull << low) - 1ull);
+        s_prefix = s_max & s_mask;
+        s_need = (unsigned int)k;
+        s_done = 0u;
+    }
+    __syncthreads();
+    while (low > 0) {
+        const int w = low < 8 ? low : 8, shift = low - w;
+        for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) hist[i] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix, mask = s_mask;
+        for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+            const unsigned long long v = keys[i];
+            if ((v & mask) == prefix) atomicAdd(&hist[warp * 256 + (int)((v >> shift) & ((1u << w) - 1u))], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            unsigned int t = 0u;
+#pragma unroll 8
+            for (int ww = 0; ww < RS_THREADS / 32; ++ww) t += hist[ww * 256 + threadIdx.x];
+            tot[threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns buckets [8 l, 8 l + 8); above[l] = keys in the buckets of the lanes above
+            unsigned int mine = 0u;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) mine += tot[8 * lane + b];
+            unsigned int above = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_down_sync(0xffffffffu, above, o);
+                if (lane + o < 32) above += v;
+            }
+            above -= mine;                                   // exclusive suffix sum
+            const unsigned int need = s_need;
+            if (above < need && above + mine >= need) {      // exactly one lane
+                unsigned int cum = above;
+                int b = 7;
+                for (; b > 0; --b) {
+                    if (cum + tot[8 * lane + b] >= need) break;
+                    cum += tot[8 * lane + b];
+                }
+                const unsigned int in_bucket = tot[8 * lane + b];
+                s_prefix = prefix | ((unsigned long long)(8 * lane + b) << shift);
+                s_mask = mask | ((unsigned long long)((1u << w) - 1u) << shift);
+                s_need = need - cum;
+                s_done = (in_bucket == need - cum) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        low = shift;
+        if (s_done) break;
+    }
+    // everything >= the k-th key: s_prefix with the undecided low bits zero (when the loop ended early the whole
+    // bucket belongs to the result; when it ran to bit 0 the prefix IS the k-th key)
+    const unsigned long long kth = s_prefix;
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+        const unsigned long long v = keys[i];
+        if (v >= kth) {
+            const unsigned int pos = atomicAdd(&s_out, 1u);
+            if (pos < (unsigned int)RS_SEL_MAX) sel[pos] = v;
+        }
+    }
+    __syncthreads();
+    return sel;
 }
 
 // exact re-scoring of the integer filter's survivors + sort.  One CTA per query: the query's fp32 table is staged
@@ -1463,7 +1570,7 @@ __device__ __forceinline__ void rescore_rows(const uint32_t* __restrict__ src, u
 //                 <= ub = sumlo + step * (T - 1 + 0.501 M + slack): keep what is STRICTLY above ub; the result is
 //                 exact iff at least k documents are kept.
 // status: 0 ok, 1 fewer than k_eff kept, 2 the approximate list overflowed, 3 too many kept for the sort
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 1)
 adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict__ codes, int M, int lut_in_smem,
                         const float* __restrict__ thr, const int* __restrict__ thr_i,
                         const float* __restrict__ qstep, const double* __restrict__ qsumlo,
@@ -1484,7 +1591,7 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
     if (lut_in_smem) {
         float* ts = reinterpret_cast<float*>(skeys + CAND_CAP);
         const float4* src4 = reinterpret_cast<const float4*>(t);
-        for (int i = threadIdx.x; i < M * (ADC_K / 4); i += SEL_THREADS) reinterpret_cast<float4*>(ts)[i] = __ldg(src4 + i);
+        for (int i = threadIdx.x; i < M * (ADC_K / 4); i += RS_THREADS) reinterpret_cast<float4*>(ts)[i] = __ldg(src4 + i);
         t = ts;
     }
     __syncthreads();
@@ -1512,7 +1619,7 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
         if (M <= 48) rescore_rows<6, 2>(src, c_approx, codes, M, t, keep);
         else rescore_rows<12, 1>(src, c_approx, codes, M, t, keep);
     } else {
-        for (unsigned int i = threadIdx.x; i < c_approx; i += SEL_THREADS) {
+        for (unsigned int i = threadIdx.x; i < c_approx; i += RS_THREADS) {
             const uint32_t doc = src[i];
             const uint8_t* cp = codes + (int64_t)doc * M;
             float sc = 0.0f;
@@ -1535,13 +1642,22 @@ adc_rescore_sort_kernel(const float* __restrict__ lut, const uint8_t* __restrict
         if (threadIdx.x == 0) status[q] = c > (unsigned int)CAND_CAP ? 3 : 1;
         return;
     }
+    // the k_eff largest of the c kept keys (all different: the document is part of the key) are selected with a radix
+    // select and only those are sorted: sorting all ~3 k_eff kept keys cost 6-13x the compare-exchanges
+    unsigned long long* sorted = skeys;
     int n = 2;
-    while (n < (int)c) n <<= 1;
-    for (int i = (int)c + threadIdx.x; i < n; i += SEL_THREADS) skeys[i] = 0ull;
-    bitonic_sort_desc(skeys, n);
-    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+    if (c > (unsigned int)k_eff && k_eff <= RS_SEL_MAX) {
+        sorted = rs_select_topk(skeys, (int)c, k_eff, reinterpret_cast<unsigned char*>(skeys + CAND_CAP));
+        while (n < k_eff) n <<= 1;
+        for (int i = k_eff + threadIdx.x; i < n; i += RS_THREADS) sorted[i] = 0ull;
+    } else {
+        while (n < (int)c) n <<= 1;
+        for (int i = (int)c + threadIdx.x; i < n; i += RS_THREADS) skeys[i] = 0ull;
+    }
+    bitonic_sort_desc(sorted, n);
+    for (int i = threadIdx.x; i < k; i += RS_THREADS) {
         if (i < k_eff) {
-            const unsigned long long key = skeys[i];
+            const unsigned long long key = sorted[i];
             scores[q * ld_s + i] = key_to_f32((uint32_t)(key >> 32));
             ids[q * ld_i + i] = id_offset + (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
         } else {
@@ -1612,7 +1728,7 @@ static AdcPlan adc_plan(int64_t nq, int64_t N, int64_t k) {
         return p;
     }
     const int64_t target = std::min<int64_t>(CAND_CAP / 2, std::max<int64_t>(3 * (int64_t)p.k_eff, 2048));
-    int64_t ns = std::max<int64_t>(32768, (64 * N + target - 1) / target);
+    int64_t ns = std::max<int64_t>(32768, (32 * N + target - 1) / target);   // threshold = ~32nd largest sample sum
     ns = (ns + SAMPLE_BLK - 1) / SAMPLE_BLK * SAMPLE_BLK;
     const int64_t nblk = ns / SAMPLE_BLK;
     p.n_sample = ns;
@@ -1821,7 +1937,7 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         const bool fields8 = int_sampling && u8_enabled(M) && codes_aligned;
         const U8Cfg u8 = u8_cfg(M);
         const int qmax = fields8 ? 255 / u8.acc : 65535 / M;
-        const int cand_cap = fields8 ? CAND_CAP32 : CAND_CAP;
+        const int cand_cap = fields8 ? cand_cap32(M) : CAND_CAP;
         if (int_sampling) {
             // fp32 tables + integer tables in the scan's shared-memory layout, one kernel
             const int qp = fields8 ? u8.eb : cf_qp(M);
@@ -1918,7 +2034,8 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         // 3. exact re-score of the survivors + per-query sort
         const size_t lut_bytes = (size_t)M * ADC_K * 4;
         const int lut_in_smem = (size_t)CAND_CAP * 8 + lut_bytes <= 200 * 1024 ? 1 : 0;
-        adc_rescore_sort_kernel<<<(unsigned)qc, SEL_THREADS, (size_t)CAND_CAP * 8 + (lut_in_smem ? lut_bytes : 0), st>>>(
+        const size_t rs_smem = (size_t)CAND_CAP * 8 + std::max(lut_in_smem ? lut_bytes : (size_t)0, RS_AUX_BYTES);
+        adc_rescore_sort_kernel<<<(unsigned)qc, RS_THREADS, rs_smem, st>>>(
             w.lut, codes, M, lut_in_smem, int_sampling ? nullptr : w.thr, w.thr_i, w.qstep, w.qsumlo, w.qsumabs, w.cand32,
             cand_cap, w.cnt, ik, p.k_eff, id_offset, scores + c0 * k, k, ids + c0 * k, k, w.status, w.exact_cnt);
         RC_CHECK_LAUNCH("adc_rescore_sort_kernel");

@@ -81,7 +81,7 @@ def search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np.ndarr
             and isinstance(corpus_ids, np.ndarray) and corpus_ids.dtype == np.int64):
         # position -> corpus id on the device, before the copy back (same values as :183)
         topk_scores, topk_ids = index.search(query_embeds, topk, corpus_ids=corpus_ids)
-        if isinstance(index, ShardedSearcher) and index.rank != 0:
+        if isinstance(index, (ShardedSearcher, ReplicatedSearcher)) and index.rank != 0:
             return topk_scores, topk_ids                     # empty on the ranks that do not receive the result
     else:
         topk_scores, topk_idx = index.search(query_embeds, topk)
@@ -100,7 +100,7 @@ def batch_search(query_ids: np.ndarray, query_embeds: np.ndarray, corpus_ids: np
         # same batches (np.array_split, :193-197), searched back to back with the copy-back of one batch
         # overlapping the scan of the next
         scores, ids = index.search_batches(np.array_split(query_embeds, iterations), topk, corpus_ids=corpus_ids)
-        # (a multi-process ShardedSearcher delivers the merged result on rank 0 only; the other ranks get empty arrays)
+        # (the multi-process searchers deliver the result on rank 0 only; the other ranks get empty arrays)
         assert len(scores) == len(ids) and len(scores) in (len(query_ids), 0)
         return scores, ids
     for query_id_iter, query_embeds_iter in tqdm(zip(
@@ -211,7 +211,63 @@ class ShardedSearcher:
                                          copy_back=self.rank == 0)
 
 
-_DEVICE_INDEXES = (faiss.GpuIndexPQ, faiss.MultiGpuIndexPQ, ShardedSearcher)
+class ReplicatedSearcher:
+    """Multi-PROCESS search over index REPLICAS (one process per GPU, every rank holds the whole index): the
+    queries are split, rank r scans the r-th block of ceil(nq / W) queries over the full corpus and one all_gather
+    of the (nq / W, k) blocks gives every rank the result.  This is the reference's own multi-GPU mode --
+    `index_cpu_to_all_gpus` with `shard = False` replicates the index and splits the queries
+    (evaluate_repconc.py:130-134) -- and the right one whenever the coded corpus fits one GPU (8.8 M x 48 B =
+    424 MB): every per-query cost (tables, threshold sample, re-score, sort) shrinks with W, and the exchange is
+    12 B x nq x k per rank instead of the per-shard lists.  Corpora beyond one GPU use ShardedSearcher."""
+
+    def __init__(self, index, group=None):
+        self.index = index
+        self.group = group
+        self.device = index.device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ntotal = index.ntotal
+        self.last_stats = None
+
+    def search(self, x, k, corpus_ids=None):
+        """CUDA tensor in (the same queries on every rank) -> CUDA tensors out on every rank; numpy in -> numpy out
+        (rank 0; see search_batches)."""
+        k = int(k)
+        if not isinstance(x, torch.Tensor):
+            return self.search_batches([np.ascontiguousarray(x, dtype=np.float32)], k, corpus_ids=corpus_ids)
+        x = x.to(self.device)
+        W = self.world
+        if W == 1:
+            out = self.index.search_tensor(x, k)
+            self.last_stats = self.index.last_stats
+            return out
+        nq = x.shape[0]
+        nb = (nq + W - 1) // W
+        lo = min(self.rank * nb, nq)
+        hi = min(lo + nb, nq)
+        s, i = self.index.search_tensor(x[lo:hi], k)
+        if hi > lo:
+            self.last_stats = self.index.last_stats
+        if hi - lo != nb:                            # last blocks: pad with empty lists
+            ps = torch.full((nb, k), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
+            pi = torch.full((nb, k), -1, dtype=i.dtype, device=i.device)
+            ps[:hi - lo], pi[:hi - lo] = s, i
+            s, i = ps, pi
+        fs = torch.empty((W * nb, k), dtype=s.dtype, device=s.device)
+        fi = torch.empty((W * nb, k), dtype=i.dtype, device=i.device)
+        dist.all_gather_into_tensor(fs, s.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(fi, i.contiguous(), group=self.group)
+        return fs[:nq], fi[:nq]
+
+    def search_tensor(self, x, k):
+        return self.search(x, k)
+
+    def search_batches(self, batches, k, corpus_ids=None):
+        return self.index.search_batches(batches, k, corpus_ids=corpus_ids, search_fn=self.search,
+                                         copy_back=self.rank == 0)
+
+
+_DEVICE_INDEXES = (faiss.GpuIndexPQ, faiss.MultiGpuIndexPQ, ShardedSearcher, ReplicatedSearcher)
 
 
 def sharded_search(shard_index, query_embeds, topk: int, group=None):

@@ -173,3 +173,49 @@ def test_sharded_search_protocol_two_ranks_gloo():
     s, i = O.adc_search(q, c, codes, 20)
     for ms, mi in (r0, r1):
         assert np.array_equal(ms, s) and np.array_equal(mi, i)
+
+
+class _OracleIndex:
+    """stands in for a GpuIndexPQ replica: the oracle's scan on CPU tensors"""
+
+    def __init__(self, c, codes):
+        self.c, self.codes = c, codes
+        self.device = torch.device("cpu")
+        self.ntotal = len(codes)
+        self.last_stats = None
+
+    def search_tensor(self, x, k):
+        from oracle import oracle as O
+        if x.shape[0] == 0:
+            return torch.empty((0, k), dtype=torch.float32), torch.empty((0, k), dtype=torch.int64)
+        s, i = O.adc_search(x.numpy(), self.c, self.codes, k)
+        return torch.from_numpy(s), torch.from_numpy(i)
+
+
+def _replica_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from repconc_b200.evaluate_repconc import ReplicatedSearcher
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    rep = ReplicatedSearcher(_OracleIndex(c, codes))
+    out = []
+    for nq in (len(q), 3, 1):                       # even split, ragged split, fewer queries than ranks
+        s, i = rep.search(torch.from_numpy(q[:nq]), 20)
+        out.append((s.numpy(), i.numpy()))
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicated_search_protocol_two_ranks_gloo():
+    """query-split over index replicas (reference evaluate_repconc.py:130-134): every rank ends with the full result"""
+    from oracle import oracle as O
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_replica_worker, args=(2, 29736, ret), nprocs=2, join=True)
+        r0, r1 = ret[0], ret[1]
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    for j, nq in enumerate((len(q), 3, 1)):
+        s, i = O.adc_search(q[:nq], c, codes, 20)
+        for r in (r0, r1):
+            assert np.array_equal(r[j][0], s) and np.array_equal(r[j][1], i)

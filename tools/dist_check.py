@@ -83,6 +83,14 @@ def main():
     s_ok = bool(np.array_equal(s.cpu().numpy(), so) and np.array_equal(i.cpu().numpy(), io))
     s_ok = s_ok and (bool(np.array_equal(hs, so) and np.array_equal(hi_, io)) if rank == 0 else len(hs) == 0)
     ok &= s_ok
+    # --- index replicas + query split (the reference's multi-GPU mode)
+    full = GpuIndexPQ(torch.from_numpy(codes_h).to(dev), torch.from_numpy(cc).to(dev))
+    rep = E.ReplicatedSearcher(full)
+    rs, ri = rep.search(torch.from_numpy(q).to(dev), 100)
+    rhs, rhi = E.batch_search(np.arange(len(q)), q, np.arange(len(codes_h), dtype=np.int64), rep, 100, 24)
+    r_ok = bool(np.array_equal(rs.cpu().numpy(), so) and np.array_equal(ri.cpu().numpy(), io))
+    r_ok = r_ok and (bool(np.array_equal(rhs, so) and np.array_equal(rhi, io)) if rank == 0 else len(rhs) == 0)
+    ok &= r_ok
     # --- peer-memory all-reduce (rc_peer_allreduce_f64) vs a rank-ordered sum of all-gathered vectors
     from repconc_b200.peer import PeerAllReduce
     n = 48 * 256
@@ -106,7 +114,7 @@ def main():
     dist.all_reduce(flag, dist.ReduceOp.MIN)
     if rank == 0:
         print(f"dist_check world={world}: assign_golden={a_ok} assign_baseline_size_vs_reference={b_ok} "
-              f"one_rank_unsafe_flag_dense_rerun={u_ok} sharded_adc={s_ok} "
+              f"one_rank_unsafe_flag_dense_rerun={u_ok} sharded_adc={s_ok} replicated_adc={r_ok} "
               f"peer_allreduce={'exact' if (p_used and p_ok) else ('MISMATCH' if p_used else 'unavailable (NCCL used)')} "
               f"-> {'PASS' if flag.item() == 1 else 'FAIL'}")
     dist.destroy_process_group()
