@@ -401,7 +401,8 @@ def main():
         q_e2e = np.ascontiguousarray(q_host[W:W + Ksteps].reshape(-1, D))
         qids = np.arange(len(q_e2e))
         target = sharded if world > 1 else index
-        E.batch_search(qids[:2 * SEARCH_BATCH], q_e2e[:2 * SEARCH_BATCH], corpus_ids, target, TOPK, SEARCH_BATCH)
+        # warm-up: the same call shape (staging buffers, workspaces and the device copy of the id table are steady state)
+        E.batch_search(qids, q_e2e, corpus_ids, target, TOPK, SEARCH_BATCH)
         barrier()
         t0 = time.perf_counter()
         out = E.batch_search(qids, q_e2e, corpus_ids, target, TOPK, SEARCH_BATCH)

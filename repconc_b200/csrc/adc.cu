@@ -367,38 +367,42 @@ __host__ __device__ inline int u8_pos(int m, int M, int eb, int lpd);
 
 // U8 = false: 16-bit fields, entry = QP * 2 bytes at position m;  U8 = true: 8-bit fields, entry = QP bytes at
 // position u8_pos(m) (adc_scan_u8_kernel with `lpd` lanes per document)
-constexpr int LP_THREADS = 1024;   // 4 groups of 256 threads (thread = centroid k), group g takes sub-vectors m = g, g + 4, ...
-constexpr int LP_GROUPS = LP_THREADS / 256;
+// Two launches over a (tile of QP queries) x (group of LP_MG sub-vectors) grid, so that a small query batch (a rank's
+// share of a split batch: 150 queries = 10 tiles) still fills the machine:
+//   adc_lut_tile_kernel   thread k holds centroid k: the QP inner products of each sub-vector of its group (fp32, j
+//                         ascending, multiply then add: the oracle's order), the fp32 table (the exact re-score reads
+//                         it) and min / max per (query, sub-vector)
+//   adc_pack_tile_kernel  step / sum of minima per query (every CTA recomputes them from the M extrema, in m order),
+//                         then the arithmetic of adc_quantise_lut_kernel, value for value, written as entries in the
+//                         scan's shared-memory layout
+constexpr int LP_MG = 4;   // sub-vectors per CTA
 
-template <int QP, bool U8>
-__global__ void __launch_bounds__(LP_THREADS)
-adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float* __restrict__ c, int64_t nq, int M,
-                    int ds, int qmax, int lpd, float* __restrict__ lut, uint16_t* __restrict__ qpack,
-                    float* __restrict__ step_out, double* __restrict__ sumlo_out, double* __restrict__ sumabs_out) {
+template <int QP>
+__global__ void __launch_bounds__(256)
+adc_lut_tile_kernel(const float* __restrict__ queries, int64_t ldq, const float* __restrict__ c, int64_t nq, int M,
+                    int ds, float* __restrict__ lut, float* __restrict__ q_lo, float* __restrict__ q_hi) {
     extern __shared__ __align__(16) float lp_sh[];
-    const int D = M * ds;
-    float* qs = lp_sh;                         // [D][QP]  (the QP queries of a dimension are contiguous: vector reads)
-    float* wred = qs + QP * D;                 // [M][8 warps of the group][QP][2]  per-warp min / max
-    float* q_lo = wred + (size_t)M * 8 * QP * 2;   // [QP][M]
-    float* q_hi = q_lo + QP * M;               // [QP][M]
-    float* s_step = q_hi + QP * M;             // [QP]
+    float* qs = lp_sh;                             // [LP_MG * ds][QP]  (the QP queries of a dimension are contiguous)
+    float* wred = qs + (size_t)LP_MG * ds * QP;    // [LP_MG][8 warps][QP][2]
     const int64_t tile = blockIdx.x;
+    const int m0 = blockIdx.y * LP_MG, mg = min(LP_MG, M - m0);
     const int64_t q0 = tile * QP;
     const int nqt = (int)min((int64_t)QP, nq - q0);
-    const int g = threadIdx.x >> 8, k = threadIdx.x & 255, lane = k & 31, warp = k >> 5;
-    for (int i = threadIdx.x; i < QP * D; i += LP_THREADS) {
-        const int qq = i / D, d = i - qq * D;
-        qs[d * QP + qq] = qq < nqt ? queries[(q0 + qq) * ldq + d] : 0.0f;
+    const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+    for (int i = k; i < QP * mg * ds; i += 256) {
+        const int qq = i / (mg * ds), d = i - qq * (mg * ds);
+        qs[d * QP + qq] = qq < nqt ? queries[(q0 + qq) * ldq + (int64_t)m0 * ds + d] : 0.0f;
     }
     __syncthreads();
-    for (int m = g; m < M; m += LP_GROUPS) {
+    for (int mi = 0; mi < mg; ++mi) {
+        const int m = m0 + mi;
         const float* ck = c + ((int64_t)m * ADC_K + k) * ds;
         float sacc[QP];
 #pragma unroll
         for (int qq = 0; qq < QP; ++qq) sacc[qq] = 0.0f;
         for (int j = 0; j < ds; ++j) {
             const float cj = __ldg(ck + j);
-            const float4* qv = reinterpret_cast<const float4*>(qs + (size_t)(m * ds + j) * QP);
+            const float4* qv = reinterpret_cast<const float4*>(qs + (size_t)(mi * ds + j) * QP);
 #pragma unroll
             for (int v = 0; v < QP / 4; ++v) {
                 const float4 x = qv[v];
@@ -413,29 +417,44 @@ adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float*
             if (qq < nqt) lut[((q0 + qq) * M + m) * ADC_K + k] = sacc[qq];
             const float lo = warp_min(sacc[qq]), hi = warp_max(sacc[qq]);
             if (lane == 0) {
-                wred[((m * 8 + warp) * QP + qq) * 2] = lo;
-                wred[((m * 8 + warp) * QP + qq) * 2 + 1] = hi;
+                wred[((mi * 8 + warp) * QP + qq) * 2] = lo;
+                wred[((mi * 8 + warp) * QP + qq) * 2 + 1] = hi;
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < QP * M; i += LP_THREADS) {
-        const int qq = i / M, m = i - qq * M;
-        float l = wred[((m * 8) * QP + qq) * 2], h = wred[((m * 8) * QP + qq) * 2 + 1];
+    for (int i = k; i < QP * mg; i += 256) {
+        const int qq = i / mg, mi = i - qq * mg;
+        float l = wred[((mi * 8) * QP + qq) * 2], h = wred[((mi * 8) * QP + qq) * 2 + 1];
         for (int w = 1; w < 8; ++w) {
-            l = fminf(l, wred[((m * 8 + w) * QP + qq) * 2]);
-            h = fmaxf(h, wred[((m * 8 + w) * QP + qq) * 2 + 1]);
+            l = fminf(l, wred[((mi * 8 + w) * QP + qq) * 2]);
+            h = fmaxf(h, wred[((mi * 8 + w) * QP + qq) * 2 + 1]);
         }
-        q_lo[i] = l;
-        q_hi[i] = h;
+        q_lo[(q0 + qq) * M + m0 + mi] = l;          // (rows of whole tiles: the arrays hold tiles * QP queries)
+        q_hi[(q0 + qq) * M + m0 + mi] = h;
     }
-    __syncthreads();
-    if (threadIdx.x < QP) {
-        const int qq = threadIdx.x;
+}
+
+// U8 = false: 16-bit fields, entry = QP * 2 bytes at position m;  U8 = true: 8-bit fields, entry = QP bytes at
+// position u8_pos(m) (adc_scan_u8_kernel with `lpd` lanes per document)
+template <int QP, bool U8>
+__global__ void __launch_bounds__(256)
+adc_pack_tile_kernel(const float* __restrict__ lut, const float* __restrict__ q_lo, const float* __restrict__ q_hi,
+                     int64_t nq, int M, int qmax, int lpd, uint16_t* __restrict__ qpack, float* __restrict__ step_out,
+                     double* __restrict__ sumlo_out, double* __restrict__ sumabs_out) {
+    __shared__ float s_step[QP];
+    __shared__ float s_lo[QP][LP_MG];
+    const int64_t tile = blockIdx.x;
+    const int m0 = blockIdx.y * LP_MG, mg = min(LP_MG, M - m0);
+    const int64_t q0 = tile * QP;
+    const int nqt = (int)min((int64_t)QP, nq - q0);
+    const int k = threadIdx.x;
+    if (k < QP) {
+        const int qq = k;
         float range = 0.0f;
         double sumabs = 0.0, sumlo = 0.0;
         for (int m = 0; m < M; ++m) {
-            const float l = q_lo[qq * M + m], h = q_hi[qq * M + m];
+            const float l = q_lo[(q0 + qq) * M + m], h = q_hi[(q0 + qq) * M + m];
             range = fmaxf(range, h - l);
             sumabs += (double)fmaxf(fabsf(l), fabsf(h));
             sumlo += (double)l;
@@ -443,18 +462,19 @@ adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float*
         // a degenerate (constant) table still needs a positive step
         const float step = fmaxf(range, 1e-30f) / (float)qmax;
         s_step[qq] = step;
-        if (qq < nqt) {
+        for (int mi = 0; mi < mg; ++mi) s_lo[qq][mi] = q_lo[(q0 + qq) * M + m0 + mi];
+        if (qq < nqt && blockIdx.y == 0) {
             step_out[q0 + qq] = step;
             sumlo_out[q0 + qq] = sumlo;
             sumabs_out[q0 + qq] = sumabs;
         }
     }
     __syncthreads();
-    // second sweep: quantise this thread's own column k of every (query, sub-vector) of its group and write the entries
     constexpr int FB = U8 ? 1 : 2;              // bytes per field
     constexpr int NW = QP * FB / 4;             // words per entry
     unsigned char* tp = reinterpret_cast<unsigned char*>(qpack) + (size_t)tile * M * ADC_K * QP * FB;
-    for (int m = g; m < M; m += LP_GROUPS) {
+    for (int mi = 0; mi < mg; ++mi) {
+        const int m = m0 + mi;
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) w[i] = 0u;
@@ -463,7 +483,7 @@ adc_lut_pack_kernel(const float* __restrict__ queries, int64_t ldq, const float*
             int qi = 0;
             if (qq < nqt) {
                 const float v = lut[((q0 + qq) * M + m) * ADC_K + k];
-                qi = __float2int_rn((v - q_lo[qq * M + m]) / s_step[qq]);
+                qi = __float2int_rn((v - s_lo[qq][mi]) / s_step[qq]);
                 qi = qi < 0 ? 0 : (qi > qmax ? qmax : qi);
             }
             if constexpr (U8) w[qq >> 2] |= (uint32_t)qi << (8 * (qq & 3));
@@ -1747,6 +1767,7 @@ struct AdcWs {
     uint16_t* qlut; float* qstep; double* qsumlo; double* qsumabs; int* thr_i; uint32_t* cand32;
     unsigned int* exact_cnt;
     unsigned int* item_ctr;      // 2 work-item counters (sample scan, corpus scan)
+    float* q_lo; float* q_hi;    // (whole tiles of queries, M) extrema of the fp32 tables
 };
 
 static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPlan& p, void* base, AdcWs* w) {
@@ -1774,11 +1795,15 @@ static size_t adc_ws_layout(int64_t nq, int64_t N, int M, int64_t k, const AdcPl
     const size_t o_qo = take((size_t)qc * 8);
     const size_t o_qa = take((size_t)qc * 8);
     const size_t o_ti = take((size_t)qc * 4);
-    const size_t o_c32 = take((size_t)qc * CAND_CAP32 * 4);
+    const size_t o_c32 = take((size_t)qc * (u8_eb(M) ? cand_cap32(M) : CAND_CAP) * 4);
     const size_t o_ec = take((size_t)qc * 4);
     const size_t o_ic = take(16);
+    const size_t o_lo = take((size_t)((qc + 15) / 16 * 16) * M * 4);
+    const size_t o_hi = take((size_t)((qc + 15) / 16 * 16) * M * 4);
     if (w) {
         w->item_ctr = (unsigned int*)(b + o_ic);
+        w->q_lo = (float*)(b + o_lo);
+        w->q_hi = (float*)(b + o_hi);
         w->qlut = (uint16_t*)(b + o_ql);
         w->qstep = (float*)(b + o_qs);
         w->qsumlo = (double*)(b + o_qo);
@@ -1939,30 +1964,28 @@ RC_API int rc_adc_search(const float* queries, int64_t ldq, const float* centroi
         const int qmax = fields8 ? 255 / u8.acc : 65535 / M;
         const int cand_cap = fields8 ? cand_cap32(M) : CAND_CAP;
         if (int_sampling) {
-            // fp32 tables + integer tables in the scan's shared-memory layout, one kernel
+            // fp32 tables + integer tables in the scan's shared-memory layout
             const int qp = fields8 ? u8.eb : cf_qp(M);
             const unsigned tiles = (unsigned)((qc + qp - 1) / qp);
-            const size_t sm = ((size_t)qp * M * ds + (size_t)M * 8 * qp * 2 + 2 * (size_t)qp * M + qp) * 4;
-            static unsigned long long attr_seen = 0ull;
-            if (first_use_on_device(attr_seen)) {
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                RC_CUDA(cudaFuncSetAttribute(adc_lut_pack_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            }
-            if (sm > 160 * 1024) {
-                set_error("rc_adc_search: query dimension %d too large for the table builder", M * ds);
+            const dim3 grid(tiles, (unsigned)((M + LP_MG - 1) / LP_MG));
+            const size_t sm = ((size_t)LP_MG * ds * qp + (size_t)LP_MG * 8 * qp * 2) * 4;
+            if (sm > 48 * 1024) {
+                set_error("rc_adc_search: sub-vector dimension %d too large for the table builder", ds);
                 return RC_E_UNSUPPORTED;
             }
-#define RC_LUT_PACK(QP, U8)                                                                                          \
-    adc_lut_pack_kernel<QP, U8><<<tiles, LP_THREADS, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, qmax, u8.lpd, \
-                                                       w.lut, w.qlut, w.qstep, w.qsumlo, w.qsumabs)
-            if (fields8 && qp == 16) RC_LUT_PACK(16, true);
-            else if (fields8) RC_LUT_PACK(8, true);
-            else if (qp == 8) RC_LUT_PACK(8, false);
-            else RC_LUT_PACK(4, false);
-#undef RC_LUT_PACK
-            RC_CHECK_LAUNCH("adc_lut_pack_kernel");
+            if (qp == 16) adc_lut_tile_kernel<16><<<grid, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, w.q_lo, w.q_hi);
+            else if (qp == 8) adc_lut_tile_kernel<8><<<grid, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, w.q_lo, w.q_hi);
+            else adc_lut_tile_kernel<4><<<grid, 256, sm, st>>>(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, w.q_lo, w.q_hi);
+            RC_CHECK_LAUNCH("adc_lut_tile_kernel");
+#define RC_PACK(QP, U8)                                                                                            \
+    adc_pack_tile_kernel<QP, U8><<<grid, 256, 0, st>>>(w.lut, w.q_lo, w.q_hi, qc, M, qmax, u8.lpd, w.qlut, w.qstep, \
+                                                       w.qsumlo, w.qsumabs)
+            if (fields8 && qp == 16) RC_PACK(16, true);
+            else if (fields8) RC_PACK(8, true);
+            else if (qp == 8) RC_PACK(8, false);
+            else RC_PACK(4, false);
+#undef RC_PACK
+            RC_CHECK_LAUNCH("adc_pack_tile_kernel");
         } else {
             rc = launch_lut(queries + c0 * ldq, ldq, centroids, qc, M, ds, w.lut, st);
             if (rc) return rc;

@@ -253,11 +253,13 @@ class ReplicatedSearcher:
             pi = torch.full((nb, k), -1, dtype=i.dtype, device=i.device)
             ps[:hi - lo], pi[:hi - lo] = s, i
             s, i = ps, pi
-        fs = torch.empty((W * nb, k), dtype=s.dtype, device=s.device)
-        fi = torch.empty((W * nb, k), dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(fs, s.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(fi, i.contiguous(), group=self.group)
-        return fs[:nq], fi[:nq]
+        # one collective for both arrays: (nb, 3k) int32 rows = [score bits | id as two words]
+        mine = torch.cat((s.contiguous().view(torch.int32), i.contiguous().view(torch.int32)), dim=1)
+        allr = torch.empty((W * nb, 3 * k), dtype=torch.int32, device=s.device)
+        dist.all_gather_into_tensor(allr, mine, group=self.group)
+        fs = allr[:nq, :k].contiguous().view(torch.float32)
+        fi = allr[:nq, k:].contiguous().view(torch.int64)
+        return fs, fi
 
     def search_tensor(self, x, k):
         return self.search(x, k)

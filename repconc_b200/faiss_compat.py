@@ -146,6 +146,9 @@ class IndexIVFPQ(IndexPQ):
     nlist = 1
 
 
+_PINNED = {}     # (device index, name) -> page-locked staging buffer, see GpuIndexPQ._pinned
+
+
 class GpuIndexPQ:
     """Device-resident PQ index: codes (N, M) uint8 and centroids (M, 256, dsub) fp32 in HBM.
     `search` accepts numpy arrays (returns numpy) or CUDA tensors (returns CUDA tensors, as
@@ -237,10 +240,13 @@ class GpuIndexPQ:
         """persistent page-locked staging buffers (allocated once, grown on demand): host arrays go through
         them so that both directions are single asynchronous DMA copies"""
         n = int(np.prod(shape))
-        buf = self._stage.get(name)
+        key = (self.device.index, name)
+        buf = _PINNED.get(key)
         if buf is None or buf.numel() < n or buf.dtype != dtype:
+            # page-locking is slow (tens of ms, and it synchronises the device): the buffers are shared by all the
+            # index objects of a process on this device and only ever grow
             buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
-            self._stage[name] = buf
+            _PINNED[key] = buf
         return buf[:n].view(shape)
 
     def _resident_ids(self, corpus_ids):
@@ -251,9 +257,22 @@ class GpuIndexPQ:
         if a.dtype != np.int64:
             return None
         hit = self._ids_cache
-        if not hit or hit["host"].shape != a.shape or not np.array_equal(hit["host"], a):
+        if not hit or hit["host"].shape != a.shape or not self._equal_parallel(hit["host"], a):
             self._ids_cache = {"host": a.copy(), "dev": torch.from_numpy(a).to(self.device)}
         return self._ids_cache["dev"]
+
+    def _equal_parallel(self, a, b):
+        """a == b everywhere (same shape, contiguous), the comparison split over four threads (numpy releases the GIL)"""
+        if getattr(self, "_cmp_pool", None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._cmp_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="repconc-cmp")
+        a, b = a.reshape(-1), b.reshape(-1)
+        n = a.shape[0]
+        if n < (1 << 20):
+            return bool(np.array_equal(a, b))
+        cuts = [n * i // 4 for i in range(5)]
+        return all(self._cmp_pool.map(lambda j: bool(np.array_equal(a[cuts[j]:cuts[j + 1]], b[cuts[j]:cuts[j + 1]])),
+                                      range(4)))
 
     def search(self, x, k, corpus_ids=None):
         """Faiss `index.search(x, k)`.  With `corpus_ids` (int64 array) the returned ids are
@@ -317,10 +336,23 @@ class GpuIndexPQ:
                 self._drain_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="repconc-drain")
                 self._stage_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="repconc-stage")
             dev_index = self.device.index
+            # external id table: the cached device copy is used at once (optimistically) while the helper validates
+            # it against the caller's array -- a full comparison, ~10 ms per 100 MB spread over four threads --; a
+            # stale cache is detected before anything is returned and the call is simply repeated with the fresh copy
+            hit = self._ids_cache
+            a_ids = np.ascontiguousarray(corpus_ids) if (corpus_ids is not None and copy_back) else None
+            optimistic = (hit["dev"] if (a_ids is not None and hit and a_ids.dtype == np.int64
+                                         and hit["host"].shape == a_ids.shape) else None)
 
             def resident_ids():
                 with torch.cuda.device(dev_index):
-                    return self._resident_ids(corpus_ids)
+                    if a_ids.dtype != np.int64:
+                        return None, False
+                    cur = self._ids_cache
+                    if cur and cur["host"].shape == a_ids.shape and self._equal_parallel(cur["host"], a_ids):
+                        return cur["dev"], False
+                    self._ids_cache = {"host": a_ids.copy(), "dev": torch.from_numpy(a_ids).to(self.device)}
+                    return self._ids_cache["dev"], True
 
             busy = [None, None]     # per staging slot: future of the drain that still reads it
             lo = 0
@@ -406,7 +438,7 @@ class GpuIndexPQ:
                     continue
                 if ids_future is not None:
                     if ids_dev is None:
-                        ids_dev = ids_future.result()
+                        ids_dev = optimistic if optimistic is not None else ids_future.result()[0]
                         if ids_dev is None:
                             raise TypeError("search_batches: corpus_ids must be an int64 array")
                     mapped = torch.empty_like(i)
@@ -432,6 +464,11 @@ class GpuIndexPQ:
                 if f is not None:
                     f.result()
             mark("drained")
+            stale = ids_future is not None and optimistic is not None and ids_future.result()[1]
+            mark("validated")
+            if stale:
+                # the caller's id table had changed since it was cached: repeat with the refreshed device copy
+                return self.search_batches(batches, k, corpus_ids=corpus_ids, search_fn=search_fn, copy_back=copy_back)
         return out_s, out_i
 
 

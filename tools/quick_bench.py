@@ -34,7 +34,7 @@ if "adc" in what:
     N = int(os.environ.get("QB_N", 8841823))
     cases = [(48, 1200, 1000), (32, 1200, 1000), (64, 1200, 1000), (96, 1200, 1000), (48, 128, 200)]
     if os.environ.get("QB_M"):
-        cases = [(int(m), 1200, 1000) for m in os.environ["QB_M"].split(",")]
+        cases = [(int(m), int(os.environ.get("QB_NQ", 1200)), 1000) for m in os.environ["QB_M"].split(",")]
     _lib.load().rc_adc_enable_timing(1)
     for (M, nq, k) in cases:
         ds = 768 // M
