@@ -58,6 +58,21 @@ int64_t rc_launch_count(void);
 int rc_nn_assign(const float* x, int64_t ldx, const float* centroids, int64_t B, int M, int K, int ds,
                  int64_t* codes_mb, uint8_t* codes_u8, void* stream);
 
+/* f3 -- fused corpus-encode epilogue: what RepCONC.forward does after the encoder when
+ * use_constraint is False -- `dense_embed @ rotation.T` (modeling_repconc.py:98), the per-sub-vector L2
+ * normalisation of METRIC_CENTROID_COS (:99-100), `quantize` = argmin of the squared distances (:101, :51-52)
+ * -- and evaluate_repconc.py:69's `.cpu().numpy().astype(np.uint8)`, in one kernel: the rotated embeddings
+ * stay in registers, the codes come out as (B, M) uint8 rows ready for GpuIndexPQ.add.
+ *   pooled      (B, D = M*ds) fp32 encoder output, row stride ld
+ *   rotation    (D, D) fp32 row-major, y = pooled @ rotation^T (the module's `rotation` buffer)
+ *   normalize   1 for METRIC_CENTROID_COS
+ *   rotated_out optional (B, D) fp32, row stride ld_out: the module's `continuous_embeds`; NULL to skip
+ *   codes_mb / codes_u8  as for rc_nn_assign (either may be NULL, not both)
+ * An identity rotation gives rc_nn_assign's codes bit for bit. */
+int rc_encode_assign(const float* pooled, int64_t ld, const float* rotation, const float* centroids, int64_t B,
+                     int M, int K, int ds, int normalize, float* rotated_out, int64_t ld_out,
+                     int64_t* codes_mb, uint8_t* codes_u8, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a1+a3  distance table + per-sub-vector extrema
  *     replaces modeling_repconc.py:50 (table) and :76-77 (max / min over (B,K)).

@@ -139,3 +139,18 @@ def adc_scores(queries, c, codes):
     for m in range(M):
         s = _f32(s + lut[:, m, :][:, codes[:, m]])
     return s
+
+
+def encode_assign(pooled, rotation, c, normalize, nn=nn_assign):
+    """RepCONC.forward after the encoder with use_constraint = False (modeling_repconc.py:98-103):
+    rotated = pooled @ rotation.T (fp32), optional per-sub-vector L2 normalisation with F.normalize's eps = 1e-12
+    (:99-100), codes = argmin of the squared distances (:51-52).  `nn` = the NN-assign restatement to use
+    (this module's numpy one, or the C oracle's).  Returns (rotated (B, D) fp32, codes (B, M) int64)."""
+    pooled, rotation, c = _f32(pooled), _f32(rotation), _f32(c)
+    M = c.shape[0]
+    y = pooled @ rotation.T
+    if normalize:
+        ys = y.reshape(len(y), M, -1)
+        n = np.sqrt((ys * ys).sum(-1, keepdims=True, dtype=np.float32))
+        y = (ys / np.maximum(n, np.float32(1e-12))).reshape(len(y), -1).astype(np.float32)
+    return y, nn(np.ascontiguousarray(y), c)

@@ -53,6 +53,8 @@ SIGNATURES = {
                            c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr]),
     "rc_mse_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int,
                            c_int, c_int, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "rc_encode_assign": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_ptr, c_i64, c_ptr,
+                                 c_ptr, c_ptr]),
     "rc_adc_search_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_int, c_i64]),
     "rc_adc_search": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_i64, c_i64, c_ptr,
                               c_ptr, c_ptr, c_size, c_ptr]),

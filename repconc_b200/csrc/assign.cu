@@ -125,6 +125,226 @@ static int launch_nn(const float* x, int64_t ldx, const float* c, int64_t B, int
 }
 
 // =============================================================================================
+// f3  fused corpus-encode epilogue: rotation + optional sub-vector L2 normalisation + NN assign + uint8 pack
+//     (modeling_repconc.py:98-103 with use_constraint = False, evaluate_repconc.py:64-70)
+// One CTA = 256 rows of the pooled encoder output x one sub-vector m.  Phase 1: y[b, j] = sum_d x[b, d] * R[m DS + j, d]
+// (fp32 FMA, d ascending) as a register-tiled product (4 rows x DS/4 columns per thread), x and the DS rows of R
+// staged through shared memory in chunks of 32 dimensions; the tile goes through shared memory once so that thread b
+// ends with row b.  Phase 2 (COS metric): y /= max(||y||, 1e-12).  Phase 3: nn_assign_kernel's loop -- the squared
+// distances in the reference's fp32 order against the 256 centroids of m broadcast from shared memory, first minimum.
+// The rotated embeddings never travel to HBM unless the caller asks for them, the codes are written as the (B, M)
+// uint8 rows GpuIndexPQ.add appends.  An identity rotation (the module's initial buffer) reproduces x bit for bit
+// (products with 0 and 1 and sums with 0 are exact), hence the codes of rc_nn_assign exactly; for a learned rotation
+// the result differs from a BLAS GEMM by summation order only (1e-6 relative), as two BLAS libraries differ.
+// =============================================================================================
+constexpr int EN_KC = 32;            // dimensions per staged chunk
+constexpr int EN_XS = EN_KC + 4;     // row stride of the staged x chunk (floats): 16-byte aligned, rows 4 banks apart
+
+template <int DS, int MB>
+__global__ void __launch_bounds__(NN_THREADS)
+encode_assign_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ rot, int D,
+                     const float* __restrict__ c, int64_t B, int M, int K, int kchunk, int normalize,
+                     float* __restrict__ y_out, int64_t ldy, int64_t* __restrict__ codes_mb,
+                     uint8_t* __restrict__ codes_u8) {
+    constexpr int NC = DS * MB;                          // output columns of the CTA (MB sub-vectors)
+    static_assert(NC % 4 == 0 && NC <= 64, "4 column groups, at most 16 columns per thread");
+    constexpr int CT = NC / 4;                           // columns of the thread's register tile (4 rows x CT)
+    extern __shared__ __align__(16) float en_sh[];
+    constexpr int STAGE_FLOATS = NN_THREADS * EN_XS + EN_KC * NC;   // one stage: x chunk [256 rows][EN_XS] + R chunk [EN_KC][NC]
+    float* ys = en_sh;                                   // after the product: [NN_THREADS][NC + 1]
+    constexpr size_t YS_FLOATS = (size_t)NN_THREADS * (NC + 1) > (size_t)2 * STAGE_FLOATS
+                                     ? (size_t)NN_THREADS * (NC + 1) : (size_t)2 * STAGE_FLOATS;
+    float* cs = en_sh + YS_FLOATS;                       // phase 3: kchunk * DS floats (behind the y tile)
+    const int m0 = blockIdx.y * MB;
+    const int64_t b0 = (int64_t)blockIdx.x * NN_THREADS;
+    const int64_t b = b0 + threadIdx.x;
+    const bool live = b < B;
+    // phase 1: register-tiled product.  Thread (tr, tc) owns rows tr + 64 i (i < 4) x columns CT tc + cc: per 4
+    // dimensions it reads 4 + CT 16-byte words for 16 CT FMAs; the 8 row addresses of a warp are 36 floats apart
+    // (conflict-free), the column words are broadcast.  MB sub-vectors share one pass over x.  The chunks of 32
+    // dimensions arrive through a two-stage cp.async pipeline (x: 16-byte copies, row-major; R: 4-byte copies,
+    // transposed to dimension-major on the way in): chunk t + 1 is in flight while chunk t is multiplied.
+    const int tr = threadIdx.x >> 2, tc = threadIdx.x & 3;
+    constexpr bool PACKED = CT % 2 == 0;                 // column pairs: Blackwell FFMA2, two FMAs per lane
+    constexpr int CP = PACKED ? CT / 2 : 1;
+    f32x2_t acc2[4][CP];
+    float acc1[4][CT];                                   // odd CT (unusual sub-vector sizes): scalar FMAs
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) acc1[i][cc] = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < CP; ++cc) acc2[i][cc] = 0ull;
+    }
+    const int nchunks = (D + EN_KC - 1) / EN_KC;
+    auto issue = [&](int t) {
+        float* xs = en_sh + (size_t)(t & 1) * STAGE_FLOATS;
+        float* rs = xs + NN_THREADS * EN_XS;
+        const int d0 = t * EN_KC;
+        // x: 256 rows x 8 segments of 4 floats
+        for (int i = threadIdx.x; i < NN_THREADS * (EN_KC / 4); i += NN_THREADS) {
+            const int r = i >> 3, sg = i & 7;
+            const int64_t br = b0 + r;
+            float* dst = xs + r * EN_XS + sg * 4;
+            if (br < B && d0 + sg * 4 + 4 <= D) {
+                cp_async_16(dst, x + br * ldx + d0 + sg * 4);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    dst[e] = (br < B && d0 + sg * 4 + e < D) ? __ldg(x + br * ldx + d0 + sg * 4 + e) : 0.0f;
+            }
+        }
+        for (int i = threadIdx.x; i < NC * EN_KC; i += NN_THREADS) {
+            const int j = i / EN_KC, dd = i - j * EN_KC;
+            if (d0 + dd < D) cp_async_4(rs + dd * NC + j, rot + (int64_t)(m0 * DS + j) * D + d0 + dd);
+            else rs[dd * NC + j] = 0.0f;
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    for (int t = 0; t < nchunks; ++t) {
+        if (t + 1 < nchunks) {
+            issue(t + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* xs = en_sh + (size_t)(t & 1) * STAGE_FLOATS;
+        const float* rs = xs + NN_THREADS * EN_XS;
+#pragma unroll 2
+        for (int dd = 0; dd < EN_KC; dd += 4) {
+            float4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (tr + 64 * i) * EN_XS + dd);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if constexpr (PACKED) {
+                    f32x2_t rv2[CP];
+#pragma unroll
+                    for (int cc = 0; cc < CP; ++cc)
+                        rv2[cc] = *reinterpret_cast<const f32x2_t*>(rs + (dd + q) * NC + CT * tc + 2 * cc);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float xq = q == 0 ? xv[i].x : q == 1 ? xv[i].y : q == 2 ? xv[i].z : xv[i].w;
+                        const f32x2_t xx = pk2(xq, xq);
+#pragma unroll
+                        for (int cc = 0; cc < CP; ++cc) acc2[i][cc] = fma2_rn(xx, rv2[cc], acc2[i][cc]);
+                    }
+                } else {
+                    float rv[CT];
+#pragma unroll
+                    for (int cc = 0; cc < CT; ++cc) rv[cc] = rs[(dd + q) * NC + CT * tc + cc];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float xq = q == 0 ? xv[i].x : q == 1 ? xv[i].y : q == 2 ? xv[i].z : xv[i].w;
+#pragma unroll
+                        for (int cc = 0; cc < CT; ++cc) acc1[i][cc] = fmaf(xq, rv[cc], acc1[i][cc]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                 // the stage is refilled by the next iteration's issue
+    }
+    float acc[4][CT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (PACKED) {
+#pragma unroll
+            for (int cc = 0; cc < CP; ++cc) unpk2(acc2[i][cc], acc[i][2 * cc], acc[i][2 * cc + 1]);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < CT; ++cc) acc[i][cc] = acc1[i][cc];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) ys[(tr + 64 * i) * (NC + 1) + CT * tc + cc] = acc[i][cc];
+    __syncthreads();
+    for (int mm = 0; mm < MB; ++mm) {
+        const int m = m0 + mm;
+        float y[DS];
+#pragma unroll
+        for (int j = 0; j < DS; ++j) y[j] = ys[threadIdx.x * (NC + 1) + mm * DS + j];
+        if (normalize) {
+            float n2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < DS; ++j) n2 = fmaf(y[j], y[j], n2);
+            const float inv = fmaxf(sqrtf(n2), 1e-12f);
+#pragma unroll
+            for (int j = 0; j < DS; ++j) y[j] = y[j] / inv;
+        }
+        if (y_out && live) {
+            float* yp = y_out + b * ldy + (int64_t)m * DS;
+#pragma unroll
+            for (int j = 0; j < DS; ++j) yp[j] = y[j];
+        }
+        float best = 0.0f;
+        int bi = 0;
+        const float* cm = c + (int64_t)m * K * DS;
+        for (int k0 = 0; k0 < K; k0 += kchunk) {
+            const int kn = min(kchunk, K - k0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kn * DS; i += NN_THREADS) cs[i] = __ldg(cm + (int64_t)k0 * DS + i);
+            __syncthreads();
+            for (int kk = 0; kk < kn; ++kk) {
+                const float* ck = cs + kk * DS;
+                float d;
+                if constexpr (DS % 8 == 0) {
+                    const f32x2_t* ck2 = reinterpret_cast<const f32x2_t*>(ck);
+                    d = sqdist_aten_order_packed<DS>([&](int p) { return pk2(y[2 * p], y[2 * p + 1]); },
+                                                     [&](int p) { return ck2[p]; });
+                } else {
+                    d = sum_aten_order<DS>([&](int j) { return sqdiff(y[j], ck[j]); });
+                }
+                const int k = k0 + kk;
+                if (k == 0 || d < best || (d != d && best == best)) {   // torch.argmin: first minimum, NaN smallest
+                    best = d;
+                    bi = k;
+                }
+            }
+        }
+        if (live) {
+            if (codes_mb) codes_mb[(int64_t)m * B + b] = bi;
+            if (codes_u8) codes_u8[b * M + m] = (uint8_t)bi;
+        }
+    }
+}
+
+template <int DS, int MB>
+static int launch_encode_inst(const float* x, int64_t ldx, const float* rot, int D, const float* c, int64_t B, int M,
+                              int K, int normalize, float* y, int64_t ldy, int64_t* mb, uint8_t* u8, cudaStream_t st) {
+    constexpr int NC = DS * MB;
+    const size_t ys_floats = std::max((size_t)NN_THREADS * (NC + 1), (size_t)2 * (NN_THREADS * EN_XS + EN_KC * NC));
+    int kchunk = (16 * 1024) / (DS * 4);
+    if (kchunk > K) kchunk = K;
+    const size_t smem = (ys_floats + (size_t)kchunk * DS) * 4;
+    auto kern = encode_assign_kernel<DS, MB>;
+    static unsigned long long attr_seen = 0ull;
+    if (first_use_on_device(attr_seen))
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    dim3 grid((unsigned)((B + NN_THREADS - 1) / NN_THREADS), (unsigned)(M / MB));
+    kern<<<grid, NN_THREADS, smem, st>>>(x, ldx, rot, D, c, B, M, K, kchunk, normalize, y, ldy, mb, u8);
+    RC_CHECK_LAUNCH("encode_assign_kernel");
+    return RC_OK;
+}
+
+// sub-vectors per CTA: as many as fit 64 output columns and divide M
+template <int DS>
+static int launch_encode(const float* x, int64_t ldx, const float* rot, int D, const float* c, int64_t B, int M, int K,
+                         int normalize, float* y, int64_t ldy, int64_t* mb, uint8_t* u8, cudaStream_t st) {
+    if constexpr (DS * 4 <= 64) {
+        if (M % 4 == 0) return launch_encode_inst<DS, 4>(x, ldx, rot, D, c, B, M, K, normalize, y, ldy, mb, u8, st);
+    }
+    if constexpr (DS * 2 <= 64) {
+        if (M % 2 == 0) return launch_encode_inst<DS, 2>(x, ldx, rot, D, c, B, M, K, normalize, y, ldy, mb, u8, st);
+    }
+    return launch_encode_inst<DS, 1>(x, ldx, rot, D, c, B, M, K, normalize, y, ldy, mb, u8, st);
+}
+
+// =============================================================================================
 // a1 + a3  distance table and extrema
 // =============================================================================================
 constexpr int TB_ROWS = 64;  // rows of x staged per CTA
@@ -1999,6 +2219,28 @@ RC_API int rc_nn_assign(const float* x, int64_t ldx, const float* centroids, int
     })
 #undef CALL
     return rc;
+}
+
+RC_API int rc_encode_assign(const float* pooled, int64_t ld, const float* rotation, const float* centroids, int64_t B,
+                            int M, int K, int ds, int normalize, float* rotated_out, int64_t ld_out,
+                            int64_t* codes_mb, uint8_t* codes_u8, void* stream) {
+    RC_REQUIRE(pooled && rotation && centroids && (codes_mb || codes_u8), "rc_encode_assign: null pointer");
+    RC_REQUIRE(B >= 0 && M >= 1 && K >= 1 && ds >= 1 && ld >= (int64_t)M * ds, "rc_encode_assign: bad shape");
+    RC_REQUIRE(!codes_u8 || K <= 256, "rc_encode_assign: uint8 codes need K <= 256 (K=%d)", K);
+    RC_REQUIRE(!rotated_out || ld_out >= (int64_t)M * ds, "rc_encode_assign: bad output stride");
+    RC_REQUIRE(((uintptr_t)pooled & 15) == 0 && (ld & 3) == 0 && ((uintptr_t)rotation & 3) == 0,
+               "rc_encode_assign: pooled rows must be 16-byte aligned (pointer and row stride)");
+    if (B == 0) return RC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = M * ds;
+    switch (ds) {
+#define RC_EN(DS) case DS: return launch_encode<DS>(pooled, ld, rotation, D, centroids, B, M, K, normalize, rotated_out, ld_out, codes_mb, codes_u8, st)
+        RC_EN(4); RC_EN(8); RC_EN(12); RC_EN(16); RC_EN(24); RC_EN(32);
+#undef RC_EN
+        default: break;
+    }
+    set_error("rc_encode_assign: sub-vector dimension %d is not compiled in (4, 8, 12, 16, 24, 32)", ds);
+    return RC_E_UNSUPPORTED;
 }
 
 RC_API int rc_minmax_init(float* minmax, int M, void* stream) {

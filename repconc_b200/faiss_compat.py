@@ -193,14 +193,32 @@ class GpuIndexPQ:
         encoding with `ops.nn_assign(..., uint8=True)` never has to leave HBM).  Amortised growth."""
         ops._require_cuda(new_codes, "new_codes")
         assert new_codes.dtype == torch.uint8 and new_codes.dim() == 2 and new_codes.shape[1] == self.M
-        n_old, n_new = self.ntotal, int(new_codes.shape[0])
+        self._reserve(int(new_codes.shape[0])).copy_(new_codes.to(self.device))
+
+    def _reserve(self, n_new):
+        """grow the code storage by n_new rows (amortised) and return the (n_new, M) uint8 view of the new tail"""
+        n_old = self.ntotal
         cap = getattr(self, "_cap", None)
         if cap is None or cap.shape[0] < n_old + n_new or cap.data_ptr() != self.codes.data_ptr():
             cap = torch.empty((max(2 * n_old, n_old + n_new), self.M), dtype=torch.uint8, device=self.device)
             cap[:n_old] = self.codes
             self._cap = cap
-        cap[n_old:n_old + n_new] = new_codes.to(self.device)
         self.codes = cap[: n_old + n_new]
+        return cap[n_old:n_old + n_new]
+
+    def add_encoded(self, pooled, rotation, normalize=False):
+        """Corpus encoding straight into the index: `pooled` (n, d) CUDA fp32 encoder outputs are
+        rotated, optionally normalised per sub-vector (METRIC_CENTROID_COS), NN-assigned against this index's
+        centroids and written as uint8 rows at the tail of the code storage by ONE kernel (rc_encode_assign) --
+        the device-side `model(...return_code=True)` + `.cpu().numpy().astype(np.uint8)` + `add_docs` of
+        evaluate_repconc.py:64-70,89-98.  Returns the (n, M) view of the appended codes."""
+        ops._require_cuda(pooled, "pooled")
+        n_new = int(pooled.shape[0])
+        tail = self._reserve(n_new)
+        if n_new:
+            ops.encode_assign(pooled, rotation, self.centroids, normalize=normalize, uint8=True, return_rotated=False,
+                              out=tail)
+        return tail
 
     def set_centroids(self, centroids):
         with torch.no_grad():

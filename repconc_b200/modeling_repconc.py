@@ -76,6 +76,16 @@ class RepCONC(nn.Module):
     def forward(self, input_ids, attention_mask, discrete_codes=None, return_code=False,
                 return_quantized_embedding=False):
         dense_embed = self.dense_encoder(input_ids=input_ids, attention_mask=attention_mask)
+        cos = self.config.similarity_metric == "METRIC_CENTROID_COS"
+        if (discrete_codes is None and (return_code or return_quantized_embedding) and not self.use_constraint
+                and not torch.is_grad_enabled() and dense_embed.is_cuda
+                and self.centroids.shape[-1] in ops.ENCODE_DS):
+            # corpus encoding (evaluate_repconc.py:64-70 runs under no_grad with use_constraint = False): rotation,
+            # optional normalisation and NN assign in one kernel
+            rotated_embed, discrete_codes = ops.encode_assign(dense_embed, self.rotation, self.centroids, normalize=cos)
+            quantized_embeds = self.decode(discrete_codes) if return_quantized_embedding else None
+            return QuantizeOutput(continuous_embeds=rotated_embed, quantized_embeds=quantized_embeds,
+                                  discrete_codes=discrete_codes)
         rotated_embed = dense_embed @ self.rotation.T
         if self.config.similarity_metric == "METRIC_CENTROID_COS":
             rotated_embed = F.normalize(

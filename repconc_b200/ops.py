@@ -93,6 +93,49 @@ def nn_assign(x, centroids, uint8=False):
 
 
 # ------------------------------------------------------------------------------------------
+# f3  fused encode epilogue: rotation + optional normalisation + NN assign (+ uint8 pack)
+#     (modeling_repconc.py:98-103, evaluate_repconc.py:64-70)
+# ------------------------------------------------------------------------------------------
+ENCODE_DS = (4, 8, 12, 16, 24, 32)       # sub-vector sizes rc_encode_assign is compiled for
+
+
+def encode_assign(pooled, rotation, centroids, normalize=False, uint8=False, return_rotated=True, out=None):
+    """RepCONC.forward after the encoder for use_constraint = False, in one kernel:
+        rotated = pooled @ rotation.T ; [per-sub-vector L2 normalise] ; codes = argmin_k ||rotated[:, m] - c[m, k]||^2
+    Returns (rotated (B, D) fp32 or None, codes): codes as the reference's (B, M) int64 view, or with uint8=True a
+    contiguous (B, M) uint8 tensor -- `out` (a (B, M) uint8 CUDA view, e.g. the tail of an index's code storage)
+    receives them in place."""
+    lib = _lib.load()
+    x = _rows_f32(pooled, "dense_embed")
+    c = _centroids_f32(centroids)
+    M, K, ds = _check_shapes(x, c)
+    _require_cuda(rotation, "rotation")
+    r = rotation.detach().float().contiguous()
+    D = M * ds
+    if tuple(r.shape) != (D, D):
+        raise ValueError(f"rotation {tuple(r.shape)} != ({D}, {D})")
+    if ds not in ENCODE_DS:
+        raise NotImplementedError(f"encode_assign: sub-vector dimension {ds} not in {ENCODE_DS}")
+    B = x.shape[0]
+    with torch.cuda.device(x.device):
+        rotated = torch.empty((B, D), dtype=torch.float32, device=x.device) if return_rotated else None
+        if uint8:
+            if out is None:
+                out = torch.empty((B, M), dtype=torch.uint8, device=x.device)
+            if out.dtype != torch.uint8 or tuple(out.shape) != (B, M) or not out.is_contiguous() or not out.is_cuda:
+                raise ValueError("encode_assign: `out` must be a contiguous (B, M) uint8 CUDA tensor")
+            mb, u8 = None, out.data_ptr()
+        else:
+            out = torch.empty((M, B), dtype=torch.int64, device=x.device)
+            mb, u8 = out.data_ptr(), None
+        if B:
+            _lib.check(lib.rc_encode_assign(x.data_ptr(), _ld(x), r.data_ptr(), c.data_ptr(), B, M, K, ds,
+                                            1 if normalize else 0, rotated.data_ptr() if return_rotated else None,
+                                            D, mb, u8, _stream()), "rc_encode_assign")
+    return rotated, (out if uint8 else out.t())
+
+
+# ------------------------------------------------------------------------------------------
 # a1+a3  table + extrema  (modeling_repconc.py:50,76-77)
 # ------------------------------------------------------------------------------------------
 def dist_table(x, centroids):

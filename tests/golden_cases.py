@@ -39,6 +39,14 @@ MSE_CASES = {
     "mse_n64":     dict(D=128, M=8,  K=256, n=64,  w=1e-4, scale=1.0,     seed=41),
     "mse_amp":     dict(D=768, M=48, K=256, n=64,  w=1e-4, scale=65536.0, seed=42),
 }
+# forward() after the encoder: rotation + (COS) normalisation + NN assign   (modeling_repconc.py:98-103)
+ENCODE_CASES = {
+    "enc_ip_eye":   dict(D=768, M=48, K=256, B=512, metric="METRIC_IP",           rotation="eye",    seed=61),
+    "enc_ip_rot":   dict(D=768, M=48, K=256, B=512, metric="METRIC_IP",           rotation="random", seed=62),
+    "enc_cos_rot":  dict(D=768, M=48, K=256, B=512, metric="METRIC_CENTROID_COS", rotation="random", seed=63),
+    "enc_cos_m32":  dict(D=768, M=32, K=256, B=300, metric="METRIC_CENTROID_COS", rotation="random", seed=64),
+    "enc_ip_m96":   dict(D=768, M=96, K=256, B=300, metric="METRIC_IP",           rotation="random", seed=65),
+}
 ADC_CASES = {
     "adc_m8":      dict(D=128, M=8,  K=256, N=10000, nq=64, ks=(10, 1000), seed=51),
     "adc_m48":     dict(D=768, M=48, K=256, N=4000,  nq=16, ks=(10, 100),  seed=52),
@@ -61,6 +69,23 @@ def assign_inputs(case):
         pool[: min(B, K // 2)] = x[: min(B, K // 2)]
         c = np.ascontiguousarray(pool.reshape(K, M, ds).transpose(1, 0, 2))
     return x, c
+
+
+def encode_inputs(case):
+    """pooled encoder outputs, rotation (orthogonal, or identity) and centroids (normalised rows for the COS metric,
+    as normalize_centrodis keeps them)"""
+    r = _rng(case["seed"])
+    D, M, K, B = case["D"], case["M"], case["K"], case["B"]
+    ds = D // M
+    x = r.standard_normal((B, D), dtype=np.float32)
+    c = r.standard_normal((M, K, ds), dtype=np.float32)
+    if case["metric"] == "METRIC_CENTROID_COS":
+        c = (c / np.linalg.norm(c, axis=-1, keepdims=True)).astype(np.float32)
+    if case["rotation"] == "eye":
+        rot = np.eye(D, dtype=np.float32)
+    else:
+        rot = np.linalg.qr(r.standard_normal((D, D)))[0].astype(np.float32)
+    return x, np.ascontiguousarray(rot), np.ascontiguousarray(c)
 
 
 def mse_inputs(case):

@@ -166,3 +166,21 @@ def test_warmup_oracle_properties(oracle):
     codes = oracle.nn_assign(np.ascontiguousarray(xp), c2)
     rec = W.decode(codes, c2)
     assert ((x @ A2.T - rec) ** 2).sum() <= ((x @ A.T - rec) ** 2).sum() * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("name", list(GC.ENCODE_CASES))
+def test_encode_epilogue_restatement_against_reference_forward(name):
+    """oracle_np.encode_assign (rotation + COS normalisation + NN assign) vs the reference's RepCONC.forward fixtures:
+    codes equal wherever the reference's two smallest distances are not a rounding apart (numpy's and torch's fp32
+    GEMMs may sum in different orders)."""
+    from oracle import oracle as O
+    from oracle import oracle_np as ONP
+    case = GC.ENCODE_CASES[name]
+    g = golden("encode_" + name)
+    x, rot, c = GC.encode_inputs(case)
+    assert GC.digest(x, rot, c) == str(g["input_sha"])
+    y, codes = ONP.encode_assign(x, rot, c, case["metric"] == "METRIC_CENTROID_COS", nn=O.nn_assign)
+    bad = codes != g["codes"].astype(np.int64)
+    assert not (bad & (g["gap"] >= 1e-4)).any()
+    assert bad.mean() < 1e-3
+    np.testing.assert_allclose(y[:4], g["rotated_head"], rtol=1e-4, atol=2e-6)

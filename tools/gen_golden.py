@@ -9,6 +9,8 @@ What is taken from the reference:
   * assign:  RepCONC.quantize (constraint on and off), center_distance_for_constraint,
              sinkhorn_algorithm          (modeling_repconc.py:47-85,137-165)
   * decode:  modeling_repconc.decode     (:168-184)
+  * encode:  RepCONC.forward(return_code=True) behind a dummy encoder: rotation, METRIC_CENTROID_COS
+             normalisation, NN assign    (:87-110)
   * MSE:     the expression of finetune_repconc.py:367-374 + autograd (the trainer module
              itself does not import under transformers 5.5, so the three lines are quoted)
   * ADC:     Faiss is absent -> anchor = q @ decode(codes).T with the reference's decode
@@ -157,6 +159,40 @@ def run_dist(name, case):
     print(f"assign_{name}: world={world} dist-vs-single mismatches {(codes != single).sum()}")
 
 
+def run_encode(name, case):
+    """RepCONC.forward(return_code=True) of the reference with a dummy encoder that returns the pooled embeddings:
+    codes, the rotated (normalised) embeddings' digest / head, and the relative gap between the two smallest
+    distances of every (row, sub-vector) (to adjudicate a code that differs by summation order of the rotation)."""
+    from transformers import PretrainedConfig
+    from repconc.models.repconc.modeling_repconc import RepCONC
+    x, rot, c = GC.encode_inputs(case)
+    D, M, K, B = case["D"], case["M"], case["K"], case["B"]
+    cfg = PretrainedConfig(hidden_size=D)
+    cfg.MCQ_M, cfg.MCQ_K, cfg.similarity_metric = M, K, case["metric"]
+
+    class Dummy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = cfg
+
+        def forward(self, input_ids=None, attention_mask=None):
+            return torch.from_numpy(x)
+    model = RepCONC(cfg, Dummy(), False, None, None)
+    with torch.no_grad():
+        model.centroids.copy_(torch.from_numpy(c))
+        model.rotation.copy_(torch.from_numpy(rot))
+        out = model(None, None, return_code=True)
+        y = out.continuous_embeds
+        codes = out.discrete_codes.contiguous().numpy()
+        table = ((y.reshape(B, M, 1, -1).transpose(0, 1) - model.centroids.unsqueeze(1)) ** 2).sum(-1)   # M,B,K
+        low2 = torch.topk(table, 2, dim=-1, largest=False).values
+        gap = ((low2[..., 1] - low2[..., 0]) / low2[..., 1].clamp_min(1e-30)).t().contiguous().numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"encode_{name}.npz"), input_sha=GC.digest(x, rot, c),
+                        codes=codes.astype(np.uint8), gap=gap, rotated_sha=sha_table(y.numpy()),
+                        rotated_head=y[:4].numpy())
+    print(f"{name}: codes {codes.shape}, min gap {gap.min():.3e}")
+
+
 def run_mse(name, case):
     from repconc.models.repconc.modeling_repconc import decode
     x, c, g, codes = GC.mse_inputs(case)
@@ -196,10 +232,16 @@ def main():
         for name, case in GC.ASSIGN_BIG_CASES.items():
             run_assign_big(name, case)
         return
+    if "--encode" in sys.argv:       # only the forward() epilogue cases
+        for name, case in GC.ENCODE_CASES.items():
+            run_encode(name, case)
+        return
     for name, case in GC.ASSIGN_CASES.items():
         run_assign(name, case)
     for name, case in GC.DIST_CASES.items():
         run_dist(name, case)
+    for name, case in GC.ENCODE_CASES.items():
+        run_encode(name, case)
     for name, case in GC.MSE_CASES.items():
         run_mse(name, case)
     for name, case in GC.ADC_CASES.items():
