@@ -13,6 +13,8 @@
 //   [0, 1024)                    uint32 flags[2 slots][8 slices][16]  (a slice = one CTA's share of the vector,
 //                                exchanged independently of the other slices)
 //   [1024, 1024 + 2*n*8)         double slot[2][n]
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rc {
@@ -52,7 +54,7 @@ struct PeerPtrs {
 template <int W_T>   // 0 = run-time W
 __global__ void __launch_bounds__(PEER_THREADS)
 peer_allreduce_f64_kernel(PeerPtrs peers, int rank, int W_rt, int64_t n, uint32_t seq, double* __restrict__ inout,
-                          int32_t* __restrict__ flags) {
+                          int32_t* __restrict__ flags, unsigned long long timeout_ns) {
     const int W = W_T > 0 ? W_T : W_rt;
     const int slot = (int)(seq & 1u);
     const int slice = blockIdx.x;
@@ -73,7 +75,7 @@ peer_allreduce_f64_kernel(PeerPtrs peers, int rank, int W_rt, int64_t n, uint32_
         const uint32_t* my = reinterpret_cast<const uint32_t*>(peers.base[rank]) + fidx + threadIdx.x;
         const unsigned long long t0 = global_ns();
         while ((int32_t)(ld_acquire_sys(my) - seq) < 0) {   // sequence numbers only grow (wrap-safe compare)
-            if (global_ns() - t0 > 2000000000ull) { s_timeout = 1; break; }
+            if (global_ns() - t0 > timeout_ns) { s_timeout = 1; break; }
         }
     }
     __syncthreads();
@@ -127,11 +129,19 @@ RC_API int rc_peer_allreduce_f64(const uint64_t* peer_buffers_host, int rank, in
     int slices = (int)((n + 1023) / 1024);
     if (slices > PEER_SLICES) slices = PEER_SLICES;
     cudaStream_t st = (cudaStream_t)stream;
+    // bound of the wait for a peer: env RC_PEER_TIMEOUT_MS (default 30 s -- a rank may sit in a checkpoint, a
+    // garbage collection or a debugger); on expiry RC_FLAG_PEER_TIMEOUT is raised instead of hanging the GPU
+    static unsigned long long tmo = 0ull;
+    if (tmo == 0ull) {
+        const char* e = getenv("RC_PEER_TIMEOUT_MS");
+        const double ms = (e && e[0]) ? atof(e) : 30000.0;
+        tmo = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+    }
     switch (W) {
-        case 2: peer_allreduce_f64_kernel<2><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags); break;
-        case 4: peer_allreduce_f64_kernel<4><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags); break;
-        case 8: peer_allreduce_f64_kernel<8><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags); break;
-        default: peer_allreduce_f64_kernel<0><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags);
+        case 2: peer_allreduce_f64_kernel<2><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags, tmo); break;
+        case 4: peer_allreduce_f64_kernel<4><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags, tmo); break;
+        case 8: peer_allreduce_f64_kernel<8><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags, tmo); break;
+        default: peer_allreduce_f64_kernel<0><<<slices, PEER_THREADS, 0, st>>>(pp, rank, W, n, seq, inout, flags, tmo);
     }
     RC_CHECK_LAUNCH("peer_allreduce_f64_kernel");
     return RC_OK;

@@ -394,7 +394,17 @@ def decode_forward(codes, centroids):
             rc = lib.rc_decode(codes.data_ptr(), codes.stride(0), codes.stride(1), None, c.data_ptr(), B, M, K, ds,
                                out.data_ptr(), flags.data_ptr(), _stream())
         _lib.check(rc, "rc_decode")
+        if _check_codes() and int(flags.item()) & FLAG_BADCODE:
+            # the reference's `centroids[first_indices, second_indices]` raises on an out-of-range code
+            raise IndexError(f"decode: a code is outside [0, {K})")
     return out
+
+
+def _check_codes():
+    """RC_CHECK_CODES=0 skips the read-back of the bad-code flag after rc_decode (one small device -> host copy per
+    call; out-of-range codes are then clamped silently instead of raising like the reference's indexing)."""
+    import os
+    return os.environ.get("RC_CHECK_CODES", "1") not in ("0", "false", "False")
 
 
 def decode_backward(codes, grad_q, centroid_shape):

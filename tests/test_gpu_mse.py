@@ -116,3 +116,15 @@ def test_module_surface_on_gpu(oracle):
     assert np.array_equal(model.quantize(_dev(x)).cpu().numpy(), g["codes_nn"].astype(np.int64))
     out.quantized_embeds.sum().backward()
     assert model.centroids.grad is not None and model.centroids.grad.abs().sum() > 0
+
+
+def test_decode_raises_on_out_of_range_code():
+    """the reference's `centroids[first_indices, second_indices]` (modeling_repconc.py:171-175) raises IndexError on a
+    code outside [0, K); rc_decode clamps and raises RC_FLAG_BADCODE, which ops.decode turns into the same error"""
+    from repconc_b200 import ops
+    c = torch.randn((8, 256, 16), device="cuda")
+    codes = torch.randint(0, 256, (10, 8), device="cuda")
+    ops.decode(codes, c)                                           # fine
+    codes[3, 5] = 300
+    with pytest.raises(IndexError):
+        ops.decode(codes, c)
