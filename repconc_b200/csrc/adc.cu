@@ -1548,6 +1548,7 @@ __device__ __forceinline__ unsigned long long* rs_select_topk(const unsigned lon
             }
             above -= mine;                                   // exclusive suffix sum
             const unsigned int need = s_need;
+            __syncwarp();                                    // every lane has read s_need before one of them rewrites it
             if (above < need && above + mine >= need) {      // exactly one lane
                 unsigned int cum = above;
                 int b = 7;

@@ -40,5 +40,22 @@ for N, nq, k in [(3000, 9, 17), (300_000, 20, 100)]:
     codes = torch.randint(0, 256, (N, M), generator=gen, device="cuda", dtype=torch.uint8)
     qv = torch.randn((nq, M * ds), generator=gen, device="cuda")
     s, i = GpuIndexPQ(codes, c).search_tensor(qv, k)
+# the 8-bit-field scans: 16 queries per entry with 4 and 2 lanes per document (M = 48, 32), 8 queries per entry
+# (M = 64), a ragged query tile and a ragged last split; the re-score's radix select
+for M, nq in [(48, 20), (32, 17), (64, 9)]:
+    ds = 4
+    c = torch.randn((M, 256, ds), generator=gen, device="cuda")
+    codes = torch.randint(0, 256, (270_001, M), generator=gen, device="cuda", dtype=torch.uint8)
+    qv = torch.randn((nq, M * ds), generator=gen, device="cuda")
+    s, i = GpuIndexPQ(codes, c).search_tensor(qv, 50)
+# fused encode epilogue (cp.async pipeline, packed FMA, 4 / 2 / 1 sub-vectors per CTA), appended in place
+for (B, M, ds) in [(300, 8, 16), (70, 6, 24), (129, 3, 12)]:
+    D = M * ds
+    xe = torch.randn((B, D), generator=gen, device="cuda")
+    ce = torch.randn((M, 256, ds), generator=gen, device="cuda")
+    rot = torch.linalg.qr(torch.randn((D, D), generator=gen, device="cuda"))[0].contiguous()
+    ops.encode_assign(xe, rot, ce, normalize=True)
+    idx = GpuIndexPQ(torch.empty((0, M), dtype=torch.uint8, device="cuda"), ce)
+    idx.add_encoded(xe, rot)
 torch.cuda.synchronize()
 print("sanitize_smoke done", float(s.sum()))
