@@ -977,13 +977,23 @@ adc_scan_u8_kernel(PackScanArgs a) {
         const int64_t full = (p_hi - p_lo) / DOCS_PER_IT;
         int64_t p = p_lo + warp * DPW + sub;
         const uint8_t* cp = code_ptr(p);
-        uint32_t cb[NUR], cn[NUR];
-        if (full > 0) load_codes(cp, cb);
+        // the code bytes of the next group are loaded while this one is scanned -- except where their registers
+        // (24 bytes per lane at M = 48 with 2 lanes per document, twice) would spill: there the 32 warps hide the load
+        constexpr bool PREFETCH = NUR <= 4;
+        uint32_t cb[NUR], cn[PREFETCH ? NUR : 1];
+        if (PREFETCH && full > 0) load_codes(cp, cb);
         for (int64_t t = 0; t < full; ++t) {
-            if (t + 1 < full) load_codes(SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT, cn);
-            scan_group(cb, p, true);
+            if constexpr (PREFETCH) {
+                if (t + 1 < full)
+                    load_codes(SAMPLE ? code_ptr(p + DOCS_PER_IT) : cp + (int64_t)DOCS_PER_IT * MT,
+                               reinterpret_cast<uint32_t (&)[NUR]>(cn));
+                scan_group(cb, p, true);
 #pragma unroll
-            for (int i = 0; i < NUR; ++i) cb[i] = cn[i];
+                for (int i = 0; i < NUR; ++i) cb[i] = cn[PREFETCH ? i : 0];
+            } else {
+                load_codes(SAMPLE ? code_ptr(p) : cp, cb);
+                scan_group(cb, p, true);
+            }
             p += DOCS_PER_IT;
             cp += (int64_t)DOCS_PER_IT * MT;
         }
@@ -1015,10 +1025,12 @@ static int env_int(const char* name, int dflt) {
 // select another compiled variant for A/B measurements
 struct U8Cfg { int eb, lpd, acc; };
 static U8Cfg u8_cfg(int M) {
-    U8Cfg c{u8_eb(M), 8, 2};
+    // 16-byte entries: 2 lanes per document (measured at M = 48: 17.2 ms vs 18.2 with 4 lanes, 24.3 with 8);
+    // 8-byte entries: 4 lanes (2 would put 8 documents in a phase: the byte permutation no longer fits a word)
+    U8Cfg c{u8_eb(M), 2, 2};
+    if (c.eb == 8) c.lpd = 4;
     static const int e_lpd = env_int("RC_ADC_U8_LPD", 0), e_acc = env_int("RC_ADC_U8_ACC", 0);
     if (M == 48 || M == 32 || M == 64 || M == 96) {
-        c.lpd = M == 32 ? 2 : 4;
         if (e_lpd) c.lpd = e_lpd;
         if (e_acc) c.acc = e_acc;
     }
@@ -1062,7 +1074,7 @@ static int launch_u8(PackScanArgs a, bool sample, cudaStream_t st) {
         // LSU wavefronts per group of (32 / lpd) documents x eb queries: gathers (eb / 4 per warp-wide load),
         // exchange shuffles, code loads
         const int ne = a.M / c.lpd;
-        const int shuffles = c.eb == 16 ? (c.lpd == 8 ? 7 : c.lpd == 4 ? 6 : 4) : (c.lpd == 8 ? 4 : 3);
+        const int shuffles = c.eb == 16 ? (c.lpd == 8 ? 7 : c.lpd == 4 ? 6 : 4) : (c.lpd == 8 ? 4 : 3);   // exchange steps
         const int al = ne % 8 == 0 ? 8 : ne % 4 == 0 ? 4 : ne % 2 == 0 ? 2 : 1;
         const double per_group = (double)ne * (c.eb / 4) + shuffles + (double)(ne / al);
         g_scan_wavefronts += (double)a.tiles * ((double)a.npos / (32 / c.lpd)) * per_group;
@@ -1072,9 +1084,9 @@ static int launch_u8(PackScanArgs a, bool sample, cudaStream_t st) {
     case (MT * 100 + LPD * 10 + ACC):                                        \
         return sample ? launch_u8_inst<MT, EB, LPD, ACC, true>(a, st) : launch_u8_inst<MT, EB, LPD, ACC, false>(a, st)
     switch (a.M * 100 + c.lpd * 10 + c.acc) {
-        RC_U8(8, 16, 8, 2); RC_U8(16, 16, 8, 2); RC_U8(24, 16, 8, 2); RC_U8(40, 16, 8, 2); RC_U8(80, 8, 8, 2);
-        RC_U8(32, 16, 4, 2); RC_U8(32, 16, 2, 2); RC_U8(32, 16, 8, 2);
-        RC_U8(48, 16, 4, 2); RC_U8(48, 16, 2, 2); RC_U8(48, 16, 4, 3); RC_U8(48, 16, 8, 2);
+        RC_U8(8, 16, 2, 2); RC_U8(16, 16, 2, 2); RC_U8(24, 16, 2, 2); RC_U8(40, 16, 2, 2); RC_U8(80, 8, 4, 2);
+        RC_U8(32, 16, 2, 2); RC_U8(32, 16, 4, 2);
+        RC_U8(48, 16, 2, 2); RC_U8(48, 16, 4, 2); RC_U8(48, 16, 4, 3); RC_U8(48, 16, 8, 2);
         RC_U8(64, 8, 4, 2); RC_U8(64, 8, 8, 2);
         RC_U8(96, 8, 4, 2); RC_U8(96, 8, 8, 2);
         default: break;

@@ -351,7 +351,7 @@ class GpuIndexPQ:
             # first batch is scanned.
             if getattr(self, "_drain_pool", None) is None:
                 from concurrent.futures import ThreadPoolExecutor
-                self._drain_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="repconc-drain")
+                self._drain_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="repconc-drain")
                 self._stage_pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="repconc-stage")
             dev_index = self.device.index
             # external id table: the cached device copy is used at once (optimistically) while the helper validates
@@ -376,6 +376,8 @@ class GpuIndexPQ:
             lo = 0
 
             def drain(plo, phi, slot, ev, _keep):
+                # two workers, one per staging slot: with short scans (a rank's share of a split batch) the host copy
+                # of a batch (12 B x nq x k) would otherwise take longer than the scan of the next one
                 ev.synchronize()
                 out_s[plo:phi] = self._pinned(f"s{slot}", (phi - plo, k), torch.float32).numpy()
                 out_i[plo:phi] = self._pinned(f"i{slot}", (phi - plo, k), torch.int64).numpy()

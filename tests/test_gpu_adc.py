@@ -113,7 +113,8 @@ def test_filtered_scan_path_large_corpus(oracle):
 
 
 @pytest.mark.parametrize("M,ds,N", [(32, 24, 300_000), (64, 12, 280_000), (96, 8, 270_000), (48, 16, 330_000),
-                                    (40, 4, 300_000), (12, 8, 300_000), (56, 4, 290_001)])
+                                    (40, 4, 300_000), (12, 8, 300_000), (56, 4, 290_001), (8, 16, 300_000),
+                                    (16, 8, 270_017), (24, 4, 265_000), (80, 4, 263_000)])
 def test_filtered_scan_every_kernel_family_vs_oracle(oracle, M, ds, N):
     """Above the dense-path limit (262,144 docs) every M takes sampled thresholds + a packed integer filter scan +
     exact re-score: the conflict-free kernel (M % 8 == 0), the 4-query / 2-query variants for wide codes
