@@ -169,6 +169,9 @@ int rc_sinkhorn_solve_peer(float* table, const float* minmax, int64_t B, int64_t
 /* diagnostics: per-CTA nanoseconds of the last persistent-kernel run (wait, selection, list, arrive+update);
  * out_host is a HOST array of max_ctas x 4 int64; returns the number of CTAs written; synchronises the device */
 int rc_sinkhorn_debug_cta_times(void* state, int64_t B, int M, int K, int64_t* out_host, int max_ctas);
+/* diagnostics: per sub-vector {max_k, max_k - min_k} of lu - lu_build after the last update (host array of 2*M
+ * doubles): how far the row scaling has moved since the survivor lists were selected.  Synchronises the device. */
+int rc_sinkhorn_debug_drift(void* state, int64_t B, int M, int K, double* out_host);
 int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream);
 /* apply_rowsum: 1 = apply the pending row normalisation from P first (iters >= 1); 0 = iters == 0
  * steps_done : number of rc_sinkhorn_step calls since rc_sinkhorn_begin (the last row sums get the sparse

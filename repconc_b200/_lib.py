@@ -42,6 +42,7 @@ SIGNATURES = {
                                        c_int, ctypes.c_uint32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "rc_sinkhorn_debug_cta_times": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_int]),
     "rc_sinkhorn_list_stats": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
+    "rc_sinkhorn_debug_drift": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr]),
     "rc_peer_allreduce_buffer_bytes": (c_size, [c_i64]),
     "rc_peer_allreduce_f64": (c_int, [c_ptr, c_int, c_int, c_i64, ctypes.c_uint32, c_ptr, c_ptr, c_ptr]),
     "rc_decode": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),

@@ -11,17 +11,20 @@
 //           are re-scored exactly
 //
 // Kernels (details at each definition)
-//   adc_lut_kernel            fp32 inner-product tables
-//   adc_quantise_lut_kernel   per-query integer tables (uint16, two queries per 32-bit word)
-//   adc_scan_cf_kernel        THE HOT LOOP: bank-conflict-free packed-integer filter scan, 8 queries per
-//                             16-byte shared-memory entry, a quarter-warp per document; also scans the
-//                             threshold sample (16-bit sums out)
-//   adc_scan_packed_kernel    same arithmetic, thread-per-document gather (M not a multiple of 8, M > 48)
+//   adc_lut_tile_kernel / adc_pack_tile_kernel   fp32 inner-product tables + per-query integer tables written in the
+//                             scan's shared-memory layout (a (query tile) x (sub-vector group) grid, two launches)
+//   adc_scan_u8_kernel        THE HOT LOOP: bank-conflict-free filter scan over 8-bit fields, 16 queries per 16-byte
+//                             shared-memory entry (8 per 8-byte entry for M > 48), 2 or 4 lanes per document;
+//                             also scans the threshold sample (integer sums out)
+//   adc_scan_cf_kernel        round 1's 16-bit-field version (RC_ADC_FIELDS=16, A/B measurements)
+//   adc_scan_packed_kernel    same arithmetic, thread-per-document gather (M not a multiple of 8 / 16)
+//   adc_lut_kernel / adc_quantise_lut_kernel   tables for the dense path and for the gather variant
 //   adc_scan_kernel           un-quantised fp32 scan with dense score output (small corpora, exact fallback,
 //                             fp32 sampling for the gather variant); accumulation fp32, m ascending =
 //                             bit-identical to a sequential CPU scan
-//   radix_select_*            r-th largest of a sample row (16-bit integer sums / fp32 keys)
-//   adc_rescore_sort_kernel   exact fp32 re-score of the filter's survivors + bitonic sort + exactness check
+//   radix_select_*            r-th largest of a sample row (integer sums / fp32 keys)
+//   adc_rescore_sort_kernel   exact fp32 re-score of the filter's survivors (table in shared memory) + radix select
+//                             of the k largest + bitonic sort
 //   gather_topk / sort_candidates / topk_merge   tie-exact dense top-k, per-shard list merge
 #include <float.h>
 #include <stdlib.h>
@@ -353,20 +356,13 @@ adc_scan_packed_kernel(PackScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused LUT + quantise + pack: one CTA per tile of QP queries.  Thread k holds centroid k; for every
-// sub-vector it forms the QP inner products (fp32, j ascending, multiply then add: the oracle's order),
-// writes the fp32 table (the exact re-score reads it), tracks min / max per (query, sub-vector); a second
-// sweep quantises (the arithmetic of adc_quantise_lut_kernel, value for value) and writes the tile's
-// integer tables in exactly the layout the conflict-free scan keeps in shared memory, [k][m][QP] uint16,
-// so that the scan stages a tile with a few bulk copies instead of 2-byte transposing stores.
-// Replaces adc_lut_kernel (0.44 ms per 1200 queries: one CTA per (query, sub-vector), every centroid re-read
-// per query) + adc_quantise_lut_kernel (0.09 ms).
+// fused table build for the integer filter scans.  Replaces adc_lut_kernel (0.44 ms per 1200 queries: one CTA per
+// (query, sub-vector), every centroid re-read per query) + adc_quantise_lut_kernel (0.09 ms) + the scan's own
+// transposing stage (2-byte strided shared stores per CTA) of round 1: 0.19 ms per 1200 queries.
 // ---------------------------------------------------------------------------------------------
 // (declared here, defined with the 8-bit scan) table position of sub-vector m in a tile of 8-bit fields
 __host__ __device__ inline int u8_pos(int m, int M, int eb, int lpd);
 
-// U8 = false: 16-bit fields, entry = QP * 2 bytes at position m;  U8 = true: 8-bit fields, entry = QP bytes at
-// position u8_pos(m) (adc_scan_u8_kernel with `lpd` lanes per document)
 // Two launches over a (tile of QP queries) x (group of LP_MG sub-vectors) grid, so that a small query batch (a rank's
 // share of a split batch: 150 queries = 10 tiles) still fills the machine:
 //   adc_lut_tile_kernel   thread k holds centroid k: the QP inner products of each sub-vector of its group (fp32, j

@@ -2452,6 +2452,16 @@ RC_API int rc_sinkhorn_debug_cta_times(void* state, int64_t B, int M, int K, int
     return G;
 }
 
+RC_API int rc_sinkhorn_debug_drift(void* state, int64_t B, int M, int K, double* out_host) {
+    RC_REQUIRE(state && out_host && B >= 1 && M >= 1 && K >= 1, "rc_sinkhorn_debug_drift: bad argument");
+    const SkPart p = sk_partition(B, M);
+    SkState s;
+    sk_layout(B, M, K, p, state, &s);
+    RC_CUDA(cudaDeviceSynchronize());
+    RC_CUDA(cudaMemcpy(out_host, s.drift, (size_t)M * 2 * 8, cudaMemcpyDeviceToHost));
+    return RC_OK;
+}
+
 RC_API int rc_sinkhorn_list_stats(void* state, int64_t B, int M, int K, int64_t* out, void* stream) {
     RC_REQUIRE(state && out && B >= 1 && M >= 1, "rc_sinkhorn_list_stats: bad argument");
     RC_REQUIRE(K == SP_K, "rc_sinkhorn_list_stats: survivor lists exist for K == 256 only (K=%d)", K);

@@ -267,6 +267,27 @@ def test_map_ids_on_device_matches_numpy_indexing():
     assert np.array_equal(i_map2, corpus_ids[i_pos])
 
 
+def test_batch_search_sees_in_place_id_edits_anywhere():
+    """batch_search maps ids with the cached device copy of `corpus_ids` while a helper validates it against the
+    caller's array (full comparison); an in-place edit at ANY position -- also one a sampled fingerprint would miss --
+    must show up in the results of the next call (the call is repeated with the refreshed copy)."""
+    from repconc_b200 import evaluate_repconc as E
+    case = dict(GC.ADC_CASES["adc_m8"], N=5000, nq=40)
+    q, c, codes = GC.adc_inputs(case)
+    idx = _index(c, codes)
+    corpus_ids = np.arange(5000, dtype=np.int64) * 3 + 7
+    s0, i0 = E.batch_search(np.arange(40), q, corpus_ids, idx, 20, 16)       # 3 batches -> the pipelined path
+    _, pos = idx.search(q, 20)
+    assert np.array_equal(i0, corpus_ids[pos])
+    hit = int(pos[7, 3])
+    corpus_ids[hit] = -99                                                     # a position that IS in the results
+    corpus_ids[4999 if hit != 4999 else 4998] = -7                            # and one far from any sample stride
+    s1, i1 = E.batch_search(np.arange(40), q, corpus_ids, idx, 20, 16)
+    assert np.array_equal(i1, corpus_ids[pos]) and i1[7, 3] == -99 and np.array_equal(s1, s0)
+    s2, i2 = E.batch_search(np.arange(40), q, corpus_ids, idx, 20, 16)       # steady state again
+    assert np.array_equal(i2, i1)
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (8,841,823 docs, M=48, k=1000): size-independent properties --
     sorted descending, ids unique and in range, every returned score equals an independent dense
