@@ -379,8 +379,16 @@ class GpuIndexPQ:
                 # two workers, one per staging slot: with short scans (a rank's share of a split batch) the host copy
                 # of a batch (12 B x nq x k) would otherwise take longer than the scan of the next one
                 ev.synchronize()
-                out_s[plo:phi] = self._pinned(f"s{slot}", (phi - plo, k), torch.float32).numpy()
-                out_i[plo:phi] = self._pinned(f"i{slot}", (phi - plo, k), torch.int64).numpy()
+                hs = self._pinned(f"s{slot}", (phi - plo, k), torch.float32).numpy()
+                hi_ = self._pinned(f"i{slot}", (phi - plo, k), torch.int64).numpy()
+
+                def copy_ids():
+                    out_i[plo:phi] = hi_
+                # the ids (2/3 of the bytes) on a staging helper (idle once the queries are uploaded), the scores here:
+                # the drain of the LAST batch is not overlapped by any scan
+                f = self._stage_pool.submit(copy_ids)
+                out_s[plo:phi] = hs
+                f.result()
 
             trace = getattr(self, "_trace", None)      # debugging: list that receives (label, seconds) marks
             import time as _time
