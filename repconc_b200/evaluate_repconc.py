@@ -248,25 +248,49 @@ class ReplicatedSearcher:
         s, i = self.index.search_tensor(x[lo:hi], k)
         if hi > lo:
             self.last_stats = self.index.last_stats
-        if hi - lo != nb:                            # last blocks: pad with empty lists
-            ps = torch.full((nb, k), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
-            pi = torch.full((nb, k), -1, dtype=i.dtype, device=i.device)
-            ps[:hi - lo], pi[:hi - lo] = s, i
-            s, i = ps, pi
         # one collective for both arrays: (nb, 3k) int32 rows = [score bits | id as two words]
-        mine = torch.cat((s.contiguous().view(torch.int32), i.contiguous().view(torch.int32)), dim=1)
-        allr = torch.empty((W * nb, 3 * k), dtype=torch.int32, device=s.device)
-        dist.all_gather_into_tensor(allr, mine, group=self.group)
-        fs = allr[:nq, :k].contiguous().view(torch.float32)
-        fi = allr[:nq, k:].contiguous().view(torch.int64)
-        return fs, fi
+        return self._gather_blocks(s, i, nb, nq, k)
 
     def search_tensor(self, x, k):
         return self.search(x, k)
 
+    def _gather_blocks(self, s, i, nb, nq, k):
+        """(<= nb, k) block results of every rank -> (nq, k) on every rank: one all_gather of (nb, 3k) int32 rows"""
+        W = self.world
+        n = s.shape[0]
+        if n != nb:                                  # last blocks: pad with empty lists
+            ps = torch.full((nb, k), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
+            pi = torch.full((nb, k), -1, dtype=i.dtype, device=i.device)
+            ps[:n], pi[:n] = s, i
+            s, i = ps, pi
+        mine = torch.cat((s.contiguous().view(torch.int32), i.contiguous().view(torch.int32)), dim=1)
+        allr = torch.empty((W * nb, 3 * k), dtype=torch.int32, device=s.device)
+        dist.all_gather_into_tensor(allr, mine, group=self.group)
+        return allr[:nq, :k].contiguous().view(torch.float32), allr[:nq, k:].contiguous().view(torch.int64)
+
     def search_batches(self, batches, k, corpus_ids=None):
-        return self.index.search_batches(batches, k, corpus_ids=corpus_ids, search_fn=self.search,
-                                         copy_back=self.rank == 0)
+        """host arrays in: every rank stages and uploads only ITS block of each batch (1 / W of the queries)"""
+        k = int(k)
+        W, r = self.world, self.rank
+        if W == 1:
+            return self.index.search_batches(batches, k, corpus_ids=corpus_ids)
+        full = [int(len(b)) for b in batches]
+        nbs = [(n + W - 1) // W for n in full]
+        blocks = [np.ascontiguousarray(b[min(r * nb, n): min((r + 1) * nb, n)], dtype=np.float32)
+                  for b, nb, n in zip(batches, nbs, full)]
+        todo = [j for j, n in enumerate(full) if n > 0]      # search_batches skips empty batches
+        state = {"j": 0}
+
+        def search_block(xd, kk):
+            j = todo[state["j"]]
+            state["j"] += 1
+            s, i = self.index.search_tensor(xd, kk)
+            if xd.shape[0]:
+                self.last_stats = self.index.last_stats
+            return self._gather_blocks(s, i, nbs[j], full[j], kk)
+
+        return self.index.search_batches(blocks, k, corpus_ids=corpus_ids, search_fn=search_block,
+                                         copy_back=r == 0, result_sizes=full)
 
 
 _DEVICE_INDEXES = (faiss.GpuIndexPQ, faiss.MultiGpuIndexPQ, ShardedSearcher, ReplicatedSearcher)

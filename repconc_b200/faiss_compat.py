@@ -323,7 +323,7 @@ class GpuIndexPQ:
         return hs.numpy().copy(), hi.numpy().copy()
 
 
-    def search_batches(self, batches, k, corpus_ids=None, search_fn=None, copy_back=True):
+    def search_batches(self, batches, k, corpus_ids=None, search_fn=None, copy_back=True, result_sizes=None):
         """Pipelined `search` over a list of host query arrays (the loop of evaluate_repconc.batch_search,
         `:193-203`): while the GPU scans batch i+1, the results of batch i travel device -> pinned host on a copy
         stream and are written into their slice of the preallocated output.  Returns (scores (n,k) fp32,
@@ -333,7 +333,11 @@ class GpuIndexPQ:
         (ranks other than 0 of a sharded search) and returns empty arrays."""
         k = int(k)
         search_fn = search_fn or self.search_tensor
-        sizes = [int(len(b)) for b in batches]
+        in_sizes = [int(len(b)) for b in batches]            # rows staged / uploaded per batch
+        # rows RETURNED per batch: the input sizes, unless the search function gathers more than it is given (a rank
+        # of a query-split search uploads only its block of each batch and receives the whole batch's results)
+        sizes = [int(v) for v in result_sizes] if result_sizes is not None else in_sizes
+        assert len(sizes) == len(in_sizes)
         n = sum(sizes)
         out_s = np.empty((n if copy_back else 0, k), np.float32)
         out_i = np.empty((n if copy_back else 0, k), np.int64)
@@ -407,8 +411,8 @@ class GpuIndexPQ:
             bj, row = 0, 0
             while bj < len(batches):
                 rows, b0 = 0, bj
-                while bj < len(batches) and (rows == 0 or (b0 > 0 and rows + sizes[bj] <= group_rows)):
-                    rows += sizes[bj]
+                while bj < len(batches) and (rows == 0 or (b0 > 0 and rows + in_sizes[bj] <= group_rows)):
+                    rows += in_sizes[bj]
                     bj += 1
                 groups.append((b0, bj, row, row + rows))
                 row += rows
@@ -454,13 +458,14 @@ class GpuIndexPQ:
             cur_group, xd_group, g_lo, g_hi = -1, None, 0, 0
             ids_dev = None
 
+            ilo = 0                                       # rows consumed from the staged inputs (lo: rows of results)
             for bi, xb in enumerate(batches):
-                nb = sizes[bi]
+                nb, nb_in = sizes[bi], in_sizes[bi]
                 if nb == 0:
                     continue
                 slot = bi & 1
                 mark("begin")
-                if lo >= g_hi:
+                if nb_in > 0 and ilo >= g_hi:
                     cur_group += 1
                     xd_group, up = group_future[cur_group & 1].result()
                     compute.wait_event(up)
@@ -471,7 +476,11 @@ class GpuIndexPQ:
                     if cur_group >= 1:
                         group_future[(cur_group + 1) & 1] = submit_group(cur_group + 1)
                 mark("staged")
-                xd = xd_group[lo - g_lo: lo - g_lo + nb]
+                if nb_in > 0:
+                    xd = xd_group[ilo - g_lo: ilo - g_lo + nb_in]
+                else:                                     # (a rank whose block of this batch is empty still takes part)
+                    xd = torch.empty((0, self.d), dtype=torch.float32, device=self.device)
+                ilo += nb_in
                 mark("h2d")
                 s, i = search_fn(xd, k)
                 mark("search")
