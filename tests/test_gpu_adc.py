@@ -348,3 +348,19 @@ def test_gpu_side_add_and_centroid_refresh(oracle):
     s2, i2 = idx.search(q, 10)
     o2 = oracle.adc_search(q, c2, codes, 10)
     assert np.array_equal(s2, o2[0]) and np.array_equal(i2, o2[1])
+
+
+@pytest.mark.parametrize("M,ds,N,nq,k", [(48, 4, 262_145, 1, 1), (48, 4, 300_001, 17, 2048), (32, 4, 270_000, 33, 7),
+                                          (96, 2, 265_000, 5, 2048), (64, 2, 290_000, 16, 1), (8, 8, 400_000, 49, 1000)])
+def test_filtered_scan_edge_shapes_vs_oracle(oracle, M, ds, N, nq, k):
+    """edge shapes of the filtered path: a single query (one tile with 15 empty slots), k = 1, k = 2048 (the largest k
+    the re-score's selection buffer holds), ragged tiles / splits, one document above the dense-path limit"""
+    r = np.random.default_rng(7000 + M + nq)
+    c = r.standard_normal((M, 256, ds), dtype=np.float32)
+    codes = r.integers(0, 256, size=(N, M), dtype=np.uint8)
+    q = r.standard_normal((nq, M * ds), dtype=np.float32)
+    idx = _index(c, codes)
+    s, i = idx.search(q, k)
+    os_, oi = oracle.adc_search(q, c, codes, k)
+    assert np.array_equal(s, os_) and np.array_equal(i, oi), (M, nq, k)
+    assert idx.last_stats["sample"] > 0
