@@ -423,6 +423,7 @@ def main():
         rec = {"qps": qps, "ms": ms, "e2e_qps": e2e_qps, "launches": launches, "stats": stats, "mrr": mrr,
                "n_shard": n_shard, "scan_ms": scan_ms, "scan_launches": scan_launches, "wavefronts": wavefronts,
                "alg_per_launch": alg_per_launch, "scan_avg_s": scan_avg_s, "hbm_gbs": hbm_gbs, "kernel": kname,
+               "q_per_rank": q_per_rank,
                "cpu": None}
         if do_cpu:
             nq_cpu = max(8 * cores, 32)
@@ -456,7 +457,8 @@ def main():
                 "unit": "wavefronts/clk/SM", "frac": ach,
                 "peak_source": "LSU data pipe: 1 wavefront (128 B) per clock per SM; conflict-free LDS.128 "
                                "microbenchmark profiles/r02_microbench_pipes.txt",
-                "traffic": ncu_traffic(rec["kernel"] + f"@{rec['n_shard']}"),
+                # (the committed captures are launches over a full 1200-query batch)
+                "traffic": ncu_traffic(rec["kernel"] + f"@{rec['n_shard']}") if rec["q_per_rank"] == SEARCH_BATCH else None,
                 "wavefronts_per_launch": wf, "launch_ms": rec["scan_avg_s"] * 1e3,
                 "share_of_step": rec["scan_ms"] / rec["ms"],
                 "hbm_algorithmic_frac": rec["hbm_gbs"] / hbm_peak, "hbm_algorithmic_gbs": rec["hbm_gbs"],
