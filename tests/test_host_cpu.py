@@ -211,3 +211,35 @@ def test_warmup_host_helpers_match_the_oracle():
     assert c0.shape == (3, 16, 4)
     rows = {tuple(np.round(v, 6)) for v in x.reshape(500, 3, 4)[:, 0, :]}
     assert all(tuple(np.round(v, 6)) in rows for v in c0[0].numpy())     # centroids are training points
+
+
+def _u8_pos(m, M, eb, lpd):
+    """mirror of csrc/adc.cu: u8_pos -- table position of sub-vector m in a tile of 8-bit fields"""
+    bg = 128 // eb
+    dpp, ne = bg // lpd, M // lpd
+    j, i = divmod(m, ne)
+    return bg * (i // dpp) + lpd * (i % dpp) + j
+
+
+@pytest.mark.parametrize("M,eb,lpd", [(48, 16, 2), (48, 16, 4), (48, 16, 8), (32, 16, 2), (8, 16, 2), (40, 16, 2),
+                                      (64, 8, 4), (96, 8, 4), (80, 8, 4), (64, 8, 8)])
+def test_u8_scan_layout_is_conflict_free_for_any_codes(M, eb, lpd):
+    """The invariant the 8-bit-field ADC scan rests on: with the table laid out [code][position] and
+    document slot s of a shared-memory phase walking its bytes in the order i = t ^ s, the lanes of a phase (128 bytes
+    worth of entries) hit pairwise different bank groups at EVERY step, whatever the codes are."""
+    bg = 128 // eb                      # entries per 128-byte line = lanes per phase
+    dpp, ne = bg // lpd, M // lpd       # documents per phase, code bytes per lane
+    assert sorted(_u8_pos(m, M, eb, lpd) for m in range(M)) == list(range(M))        # a permutation of the sub-vectors
+    rng = np.random.default_rng(M * 100 + eb + lpd)
+    for _ in range(50):
+        codes = rng.integers(0, 256, size=(dpp, M))
+        seen = np.zeros((dpp, M), dtype=int)
+        for t in range(ne):
+            groups = set()
+            for s in range(dpp):
+                for j in range(lpd):
+                    m = ne * j + (t ^ s)                                              # lane j's byte t ^ s
+                    seen[s, m] += 1
+                    groups.add((int(codes[s, m]) * M + _u8_pos(m, M, eb, lpd)) % bg)
+            assert len(groups) == bg, (t, groups)
+        assert (seen == 1).all()                                                      # every sub-vector exactly once
