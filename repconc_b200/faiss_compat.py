@@ -416,7 +416,6 @@ class GpuIndexPQ:
                     bj += 1
                 groups.append((b0, bj, row, row + rows))
                 row += rows
-            free_ev = [None, None]                        # per group slot: event after its last search was enqueued
 
             def load_group(gi):
                 b0, b1, r0, r1 = groups[gi]
@@ -440,21 +439,30 @@ class GpuIndexPQ:
                 # for (future + event) before searching that group: free by construction
                 return self._stage_pool.submit(load_group, gi) if gi < len(groups) else None
 
-            first = submit_group(0)
-            ids_future = self._stage_pool.submit(resident_ids) if (corpus_ids is not None and copy_back) else None
-            group_future = [first, submit_group(1)]
             # the freshly allocated output arrays are touched once by a helper while the first scans run: the page
-            # faults of their first write (~0.3 us per 4 KB page, 1-2 ms for the last batch) leave the drains
+            # faults of their first write (~0.3 us per 4 KB page, 1-2 ms for the last batch) leave the drains.
+            # Order of the helper's work: first batch's queries, first batch's output pages, id table, the rest.
             prefault = {}
+            touch_rows = []
             if copy_back and n * k >= (1 << 20):
-                def touch(plo, phi):
-                    out_s[plo:phi].fill(0)
-                    out_i[plo:phi].fill(0)
                 row = 0
                 for nb_ in sizes:                              # in batch order: a drain waits for its own slice only
                     if nb_:
-                        prefault[row] = self._stage_pool.submit(touch, row, row + nb_)
+                        touch_rows.append((row, row + nb_))
                     row += nb_
+
+            def touch(plo, phi):
+                out_s[plo:phi].fill(0)
+                out_i[plo:phi].fill(0)
+
+            first = submit_group(0)
+            if touch_rows:
+                prefault[touch_rows[0][0]] = self._stage_pool.submit(touch, *touch_rows[0])
+            ids_future = self._stage_pool.submit(resident_ids) if (corpus_ids is not None and copy_back) else None
+            group_future = [first, submit_group(1)]
+            for plo_, phi_ in touch_rows[1:]:
+                prefault[plo_] = self._stage_pool.submit(touch, plo_, phi_)
+            pos_keep = []       # (first row, rows, positions) of the batches mapped with an unvalidated id table
             cur_group, xd_group, g_lo, g_hi = -1, None, 0, 0
             ids_dev = None
 
@@ -495,6 +503,8 @@ class GpuIndexPQ:
                     mapped = torch.empty_like(i)
                     _lib.check(_lib.load().rc_map_ids(i.data_ptr(), ids_dev.data_ptr(), ids_dev.numel(), i.numel(),
                                                       mapped.data_ptr(), ops._stream()), "rc_map_ids")
+                    if optimistic is not None:
+                        pos_keep.append((lo, nb, i))         # positions, in case the cached table turns out stale
                     i = mapped
                 done = torch.cuda.Event()
                 done.record(compute)
@@ -518,8 +528,14 @@ class GpuIndexPQ:
             stale = ids_future is not None and optimistic is not None and ids_future.result()[1]
             mark("validated")
             if stale:
-                # the caller's id table had changed since it was cached: repeat with the refreshed device copy
-                return self.search_batches(batches, k, corpus_ids=corpus_ids, search_fn=search_fn, copy_back=copy_back)
+                # the caller's id table had changed since it was cached: the kept positions are mapped again with the
+                # refreshed device copy (no search is repeated, no other rank is involved)
+                fresh = ids_future.result()[0]
+                for plo, pnb, pos in pos_keep:
+                    mapped = torch.empty_like(pos)
+                    _lib.check(_lib.load().rc_map_ids(pos.data_ptr(), fresh.data_ptr(), fresh.numel(), pos.numel(),
+                                                      mapped.data_ptr(), ops._stream()), "rc_map_ids")
+                    out_i[plo:plo + pnb] = mapped.cpu().numpy()
         return out_s, out_i
 
 
