@@ -364,3 +364,34 @@ def test_filtered_scan_edge_shapes_vs_oracle(oracle, M, ds, N, nq, k):
     os_, oi = oracle.adc_search(q, c, codes, k)
     assert np.array_equal(s, os_) and np.array_equal(i, oi), (M, nq, k)
     assert idx.last_stats["sample"] > 0
+
+
+def test_single_process_multi_device_index_vs_oracle(oracle):
+    """`load_index_to_gpu(index)` from ONE process (the unchanged evaluator, run_repconc_eval.py:93-100,155) returns a
+    MultiGpuIndexPQ when several GPUs are visible: corpus shards, one host thread per device, per-shard lists merged
+    on the first device.  On a single-GPU box the shards share the device (the threading, the global ids, the
+    merge and the pipelined batch_search are the same code)."""
+    from repconc_b200 import evaluate_repconc as E
+    from repconc_b200 import faiss_compat as F
+    case = dict(GC.ADC_CASES["adc_m8"], N=7001, nq=50)
+    q, c, codes = GC.adc_inputs(case)
+    host = F.IndexPQ(case["D"], case["M"], 8, F.METRIC_INNER_PRODUCT)
+    F.copy_array_to_vector(np.ascontiguousarray(c).ravel(), host.pq.centroids)
+    host.is_trained = True
+    E.add_docs(host, codes[:4000])
+    E.add_docs(host, codes[4000:])
+    ndev = torch.cuda.device_count()
+    multi = F.MultiGpuIndexPQ.from_host(host, list(range(ndev)) if ndev >= 2 else [0, 0, 0])
+    assert multi.ntotal == 7001 and len(multi.shards) >= 2
+    corpus_ids = np.arange(7001, dtype=np.int64) * 5 + 3
+    for k in (10, 300):
+        os_, oi = oracle.adc_search(q, c, codes, k)
+        s, i = multi.search(q, k)
+        assert np.array_equal(s, os_) and np.array_equal(i, oi)
+        st, it = multi.search(_dev(q), k)                                       # CUDA tensors in -> CUDA tensors out
+        assert np.array_equal(st.cpu().numpy(), os_) and np.array_equal(it.cpu().numpy(), oi)
+        sb, ib = E.batch_search(np.arange(50), q, corpus_ids, multi, k, 16)     # 4 batches, ids mapped on the device
+        assert np.array_equal(sb, os_) and np.array_equal(ib, corpus_ids[oi])
+    if ndev >= 2:
+        assert isinstance(E.load_index_to_gpu(host), F.MultiGpuIndexPQ)
+    assert isinstance(E.load_index_to_gpu(host, 0), F.GpuIndexPQ)
