@@ -522,15 +522,39 @@ def main():
                 ev.record(copy_stream)
             return xd, ev
 
+        # results: the codes (B x M int64) and the loss of EVERY step travel to pinned host memory on a second copy
+        # stream and are read by the host one step later, while the next step computes -- a training loop that logs
+        # step i's loss after launching step i + 1; a blocking read per step would idle the GPU for the ~100 kernel
+        # launches of the following step
+        back_stream = torch.cuda.Stream(device=dev)
+        h_codes = [torch.empty((ASSIGN_B, M), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        h_loss = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+
         def e2e_loop(first, last):
             nxt = fetch(first)
+            pending, res = None, None
             for i in range(first, last):
                 xd, ev = nxt
                 if i + 1 < last:
                     nxt = fetch(i + 1)
                 torch.cuda.current_stream().wait_event(ev)
                 c_, mse_ = assign_step(xd)
-                res = c_.cpu(), float(mse_.detach())              # D2H of the codes and the loss
+                done = torch.cuda.Event()
+                done.record()
+                slot = i & 1
+                with torch.cuda.stream(back_stream):
+                    back_stream.wait_event(done)
+                    h_codes[slot].copy_(c_, non_blocking=True)       # D2H of the codes and the loss
+                    h_loss[slot].copy_(mse_.detach(), non_blocking=True)
+                    got = torch.cuda.Event()
+                    got.record(back_stream)
+                c_.record_stream(back_stream)
+                if pending is not None:
+                    pending[1].synchronize()
+                    res = h_codes[pending[0]].numpy(), float(h_loss[pending[0]])
+                pending = (slot, got)
+            pending[1].synchronize()
+            res = h_codes[pending[0]].numpy(), float(h_loss[pending[0]])
             return res
 
         e2e_loop(0, W)
