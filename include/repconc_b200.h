@@ -246,6 +246,11 @@ int rc_mse_bwd(const float* x, int64_t ldx, const float* q, int64_t ldq, const f
  * rc_adc_search runs LUT build, threshold sampling, the filtered corpus scan and the final
  * per-query sort; it SYNCHRONISES the stream (it reads per-query candidate counts back to pick
  * the exact fallback for queries whose candidate buffer under/overflowed).
+ * The corpus scan is an integer FILTER (8-bit-quantised tables, conservative threshold); every
+ * surviving document is re-scored in fp32 exactly as above and a query whose result cannot be
+ * proven complete takes an exact dense pass, so scores and ids are bit-identical to a sequential
+ * fp32 scan whatever the data.  `codes` 8-byte aligned selects the fastest scan (any alignment
+ * works); N < 2^32 per call (shard larger corpora and merge with rc_topk_merge); k <= 8192.
  * ------------------------------------------------------------------------------------------- */
 size_t rc_adc_search_workspace_bytes(int64_t nq, int64_t N, int M, int K, int64_t k);
 int rc_adc_search(const float* queries, int64_t ldq, const float* centroids, const uint8_t* codes,
