@@ -168,6 +168,8 @@ class GpuIndexPQ:
         self.metric_type = METRIC_INNER_PRODUCT
         self.is_trained = True
         self._ws = None
+        self._ws_bytes = {}
+        self._stats_buf = (_lib.c_i64 * 4)()
         self._stage = {}
         self._ids_cache = {}
         self.last_stats = None
@@ -238,20 +240,32 @@ class GpuIndexPQ:
         if x.shape[1] != self.d:
             raise ValueError(f"query width {x.shape[1]} != index dimension {self.d}")
         nq, k = x.shape[0], int(k)
-        with torch.cuda.device(self.device):
+        # (a search of a rank's share of a split batch lasts ~3 ms: the host side of a call is kept short -- no device
+        #  context switch when this index's device is already current, workspace size cached per shape)
+        switch = torch.cuda.current_device() != self.device.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.device)
+        try:
             scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
             ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
             if nq == 0:
                 return scores, ids
-            nws = lib.rc_adc_search_workspace_bytes(nq, self.ntotal, self.M, 256, k)
+            key = (nq, self.ntotal, k)
+            nws = self._ws_bytes.get(key)
+            if nws is None:
+                nws = self._ws_bytes[key] = lib.rc_adc_search_workspace_bytes(nq, self.ntotal, self.M, 256, k)
             ws = self._workspace(nws)
             _lib.check(lib.rc_adc_search(x.data_ptr(), ops._ld(x), self.centroids.data_ptr(), self.codes.data_ptr(),
                                          nq, self.ntotal, self.M, 256, self.dsub, k, self.id_offset,
                                          scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
                                          ops._stream()), "rc_adc_search")
-            st = (_lib.c_i64 * 4)()
+            st = self._stats_buf
             lib.rc_adc_last_stats(st)
             self.last_stats = dict(filtered=st[0], dense=st[1], max_candidates=st[2], sample=st[3])
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
         return scores, ids
 
     def _pinned(self, name, shape, dtype):
