@@ -591,12 +591,17 @@ def main():
                "e2e": {"value": e2e, "unit": "embeddings/s", "h2d_bytes_per_step": ASSIGN_B * D * 4,
                        "d2h_bytes_per_step": ASSIGN_B * M * 8 + 4},
                "gpu_launches": launches, "assignment_ms": t_full,
-               "roofline": {"bound": "hbm", "kernel": "sinkhorn_solve_kernel (one iteration of the persistent loop: "
-                                                       "survivor-list or selection pass + row-sum reduce / update"
+               "roofline": {"bound": "hbm", "kernel": "one Sinkhorn iteration of rc_sinkhorn_solve (survivor-list or "
+                                                       "selection pass + row-sum reduce / update"
                                                        + (" + peer exchange)" if world > 1 else ")"),
                             "achieved": alg_it / it_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_it / it_s / 1e9 / hbm_peak, "peak_source": peak_src,
                             "traffic": ncu_traffic(f"sinkhorn_iteration@M{M}"),
+                            # what the list-pass iteration physically moves (ncu DRAM bytes of one launch) over the mean
+                            # iteration time and the measured peak: the fraction to improve (the pass is latency-bound)
+                            "hbm_physical_frac": (ncu_traffic(f"sinkhorn_iteration@M{M}") / it_s / 1e9 / hbm_peak
+                                                  if ncu_traffic(f"sinkhorn_iteration@M{M}") and it_s > 0 else None),
+                            "kernel_name": "sinkhorn_step_kernel + sinkhorn_reduce_update_kernel (launch chain)",
                             "algorithmic_bytes_per_launch": alg_it, "launch_ms": it_s * 1e3,
                             "step_hbm_algorithmic_frac": alg_step / (ms / Ksteps / 1e3) / 1e9 / hbm_peak,
                             "note": "algorithmic bytes = the fp32 table read once per half-iteration (SURVEY 8d); the "
