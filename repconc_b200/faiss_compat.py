@@ -469,13 +469,22 @@ class GpuIndexPQ:
                 out_s[plo:phi].fill(0)
                 out_i[plo:phi].fill(0)
 
+            touched = [0]
+
+            def touch_ahead(upto):
+                # rolling: the output pages of the next two batches, not a backlog of every batch in front of the
+                # helpers' other work (query staging, the id halves of the drains)
+                while touched[0] < min(upto, len(touch_rows)):
+                    plo_, phi_ = touch_rows[touched[0]]
+                    prefault[plo_] = self._stage_pool.submit(touch, plo_, phi_)
+                    touched[0] += 1
+
             first = submit_group(0)
-            if touch_rows:
-                prefault[touch_rows[0][0]] = self._stage_pool.submit(touch, *touch_rows[0])
+            touch_ahead(1)
             ids_future = self._stage_pool.submit(resident_ids) if (corpus_ids is not None and copy_back) else None
             group_future = [first, submit_group(1)]
-            for plo_, phi_ in touch_rows[1:]:
-                prefault[plo_] = self._stage_pool.submit(touch, plo_, phi_)
+            touch_ahead(2)
+            n_done = 0
             pos_keep = []       # (first row, rows, positions) of the batches mapped with an unvalidated id table
             cur_group, xd_group, g_lo, g_hi = -1, None, 0, 0
             ids_dev = None
@@ -487,6 +496,8 @@ class GpuIndexPQ:
                     continue
                 slot = bi & 1
                 mark("begin")
+                n_done += 1
+                touch_ahead(n_done + 2)
                 if nb_in > 0 and ilo >= g_hi:
                     cur_group += 1
                     xd_group, up = group_future[cur_group & 1].result()
