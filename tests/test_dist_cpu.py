@@ -192,6 +192,57 @@ class _OracleIndex:
         return torch.from_numpy(s), torch.from_numpy(i)
 
 
+def _oracle_search_batches(self, batches, k, corpus_ids=None, search_fn=None, copy_back=True, result_sizes=None):
+    """CPU stand-in for GpuIndexPQ.search_batches (no pinned memory, no streams): same contract -- `batches` are the
+    rows this rank uploads, `result_sizes` the rows every batch returns, empty batches are skipped, only
+    `copy_back` ranks receive arrays"""
+    sizes = [int(v) for v in result_sizes] if result_sizes is not None else [len(b) for b in batches]
+    outs, outi = [], []
+    for b, n in zip(batches, sizes):
+        if n == 0:
+            continue
+        s, i = search_fn(torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)), k)
+        assert tuple(s.shape) == (n, k)
+        if copy_back:
+            ids = i.numpy()
+            outs.append(s.numpy())
+            outi.append(corpus_ids[ids] if corpus_ids is not None else ids)
+    if not copy_back:
+        return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+    return np.concatenate(outs), np.concatenate(outi)
+
+
+_OracleIndex.search_batches = _oracle_search_batches
+
+
+def _replica_batches_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from repconc_b200.evaluate_repconc import ReplicatedSearcher
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    rep = ReplicatedSearcher(_OracleIndex(c, codes))
+    corpus_ids = np.arange(len(codes), dtype=np.int64) * 3 + 11
+    # ragged batches, an empty one, and a batch with fewer queries than ranks
+    batches = [q[:25], q[25:25], q[25:26], q[26:64]]
+    ret[rank] = rep.search_batches(batches, 20, corpus_ids=corpus_ids)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicated_batch_search_uploads_blocks_and_returns_whole_batches_gloo():
+    """ReplicatedSearcher.search_batches: every rank passes only ITS block of each batch down, receives the gathered
+    results of the whole batch, and only rank 0 gets arrays (ids mapped through corpus_ids)"""
+    from oracle import oracle as O
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_replica_batches_worker, args=(2, 29738, ret), nprocs=2, join=True)
+        r0, r1 = ret[0], ret[1]
+    q, c, codes = GC.adc_inputs(GC.ADC_CASES["adc_m8"])
+    s, i = O.adc_search(q[:64], c, codes, 20)
+    assert np.array_equal(r0[0], s) and np.array_equal(r0[1], i * 3 + 11)
+    assert len(r1[0]) == 0 and len(r1[1]) == 0
+
+
 def _replica_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
