@@ -243,3 +243,44 @@ def test_u8_scan_layout_is_conflict_free_for_any_codes(M, eb, lpd):
                     groups.add((int(codes[s, m]) * M + _u8_pos(m, M, eb, lpd)) % bg)
             assert len(groups) == bg, (t, groups)
         assert (seen == 1).all()                                                      # every sub-vector exactly once
+
+
+@pytest.mark.parametrize("M,acc", [(48, 2), (32, 2), (96, 2), (8, 2), (48, 3)])
+def test_u8_filter_bound_never_excludes_a_better_document(M, acc):
+    """The exactness argument of the 8-bit-field ADC filter, replayed in numpy with the kernels'
+    arithmetic: tables quantised to q = clamp(round((v - lo_m) / step), 0, QMAX), step = max_m range / QMAX,
+    QMAX = 255 / acc.  For EVERY document  |exact - (sum lo + step * sum q)| <= step * (0.501 M + slack), hence a
+    document with integer sum <= T - 1 cannot beat ub = sum lo + step * (T - 1 + 0.501 M + slack): keeping what is
+    strictly above ub loses nothing."""
+    rng = np.random.default_rng(M * 10 + acc)
+    qmax = 255 // acc
+    N = 20000
+    for trial in range(3):
+        scale = [1.0, 37.5, 1e-3][trial]
+        lut = (rng.standard_normal((M, 256)) * scale).astype(np.float32)
+        if trial == 2:
+            lut[0] *= 50                                        # one sub-vector dominates the range
+        codes = rng.integers(0, 256, size=(N, M))
+        lo = lut.min(1)
+        rng_m = (lut.max(1) - lo).max()
+        step = np.float32(max(rng_m, 1e-30)) / np.float32(qmax)
+        q8 = np.clip(np.rint((lut - lo[:, None]) / step), 0, qmax).astype(np.int64)
+        assert q8.max() <= qmax and acc * qmax <= 255          # `acc` entries add up inside a byte
+        exact = np.zeros(N, dtype=np.float32)
+        for m in range(M):                                     # fp32, m ascending, like the scan / the oracle
+            exact = (exact + lut[m, codes[:, m]]).astype(np.float32)
+        s8 = q8[np.arange(M)[None, :], codes].sum(1)
+        sumlo = lo.astype(np.float64).sum()
+        sumabs = np.maximum(np.abs(lo), np.abs(lut.max(1))).astype(np.float64).sum()
+        slack = M * 1.2e-7 * sumabs / float(step) + 1.0
+        err = np.abs(exact.astype(np.float64) - (sumlo + float(step) * s8))
+        assert (err <= float(step) * (0.501 * M + slack)).all()
+        # threshold from the r-th largest integer sum, shifted as adc_u8_threshold_kernel does
+        k = 100
+        T = int(np.sort(s8)[-3 * k]) - int(np.ceil(0.501 * M + slack)) - 1
+        ub = sumlo + float(step) * (T - 1 + 0.501 * M + slack)
+        excluded = s8 <= T - 1
+        assert (exact[excluded].astype(np.float64) <= ub).all()
+        kept = (~excluded) & (exact.astype(np.float64) > ub)
+        topk = np.argsort(-exact, kind="stable")[:k]
+        assert kept.sum() >= k and kept[topk].all()
